@@ -1,0 +1,166 @@
+"""ur_conv_gemm (tcgen05 implicit GEMM) against a plain fp32 PyTorch conv/linear on the same
+bf16-rounded operands.  Tolerance: rel-L2 <= 1e-3 after rounding the reference to bf16 too
+(identical rounding points: bf16 operands, fp32 accumulate, one bf16 rounding of the output)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_close, bf16_round
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(_dev())
+
+
+def _nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def _ref_out(y_nchw):
+    return bf16_round(y_nchw.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("M,K,N", [(256, 128, 128), (128, 64, 64), (300, 320, 320), (77, 1024, 640),
+                                   (4096, 320, 960), (130, 512, 256), (512, 256, 1024), (64, 1280, 1280),
+                                   (200, 192, 72)])
+def test_linear(M, K, N):
+    from unirestore_b200 import ops
+    x, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    y = ops.conv_gemm(xb, wb, N, bias=b)
+    ref = bf16_round(F.linear(xb.float(), wb.float(), b))
+    assert_close(y, ref, TOL, "linear %dx%dx%d" % (M, K, N))
+
+
+def test_linear_residual_fp32_out_alpha():
+    from unirestore_b200 import ops
+    M, K, N = 384, 256, 320
+    x, w, r = _rand(M, K, seed=4), _rand(N, K, seed=5, scale=K ** -0.5), _rand(M, N, seed=6)
+    xb, wb, rb = x.to(torch.bfloat16), w.to(torch.bfloat16), r.to(torch.bfloat16)
+    y = ops.conv_gemm(xb, wb, N, residual=rb, alpha=0.125, out_dtype=torch.float32)
+    ref = 0.125 * F.linear(xb.float(), wb.float()) + rb.float()
+    assert y.dtype == torch.float32
+    assert_close(y, ref, 1e-5, "linear alpha+residual fp32")
+
+
+@pytest.mark.parametrize("act", ["silu", "gelu"])
+def test_linear_act_chscale(act):
+    from unirestore_b200 import ops
+    M, K, N = 2 * 96, 128, 256
+    x, w, b = _rand(2, 96, K, seed=7), _rand(N, K, seed=8, scale=K ** -0.5), _rand(N, seed=9)
+    cs, rv = _rand(2, N, seed=10), _rand(2, N, seed=11)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    y = ops.conv_gemm(xb, wb, N, bias=b, rowvec=rv, chscale=cs,
+                      act=ops.UR_ACT_SILU if act == "silu" else ops.UR_ACT_GELU)
+    pre = F.linear(xb.float(), wb.float(), b) + rv[:, None, :]
+    ref = bf16_round((F.silu(pre) if act == "silu" else F.gelu(pre)) * cs[:, None, :])
+    assert_close(y, ref, TOL, "linear act=%s chscale" % act)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (1, 24, 40, 128, 320), (3, 8, 8, 320, 640),
+                                            (2, 2, 2, 1280, 1280), (1, 64, 64, 320, 320), (5, 4, 4, 256, 512),
+                                            (1, 20, 136, 64, 128)])
+def test_conv3x3(B, H, W, Cin, Cout):
+    from unirestore_b200 import ops
+    x = _rand(B, Cin, H, W, seed=20)
+    w = _rand(Cout, Cin, 3, 3, seed=21, scale=(9 * Cin) ** -0.5)
+    b = _rand(Cout, seed=22)
+    xb, wb = _nhwc(x), w.to(torch.bfloat16)
+    y = ops.conv_gemm(xb, ops.pack_conv_weight(wb), Cout, taps=ops.TAPS_3x3, bias=b)
+    ref = _ref_out(F.conv2d(xb.float().permute(0, 3, 1, 2), wb.float(), b, padding=1))
+    assert_close(y, ref, TOL, "conv3x3 %s" % ((B, H, W, Cin, Cout),))
+
+
+@pytest.mark.parametrize("asym", [False, True])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (1, 24, 40, 128), (2, 64, 64, 320), (1, 6, 10, 256)])
+def test_conv3x3_stride2(B, H, W, C, asym):
+    from unirestore_b200 import ops
+    x = _rand(B, C, H, W, seed=30)
+    w = _rand(C, C, 3, 3, seed=31, scale=(9 * C) ** -0.5)
+    b = _rand(C, seed=32)
+    xb, wb = _nhwc(x), w.to(torch.bfloat16)
+    xin = xb.float().permute(0, 3, 1, 2)
+    if asym:   # diffusers Downsample2D(padding=0): F.pad (0,1,0,1) then stride 2 (VAE encoder, autoencoder.py:19)
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wb.float(), b, stride=2)
+        taps = ops.TAPS_3x3_NOPAD
+    else:
+        ref = F.conv2d(xin, wb.float(), b, stride=2, padding=1)
+        taps = ops.TAPS_3x3
+    y = ops.conv_gemm(xb, ops.pack_conv_weight(wb), C, taps=taps, stride=2, hout=ref.shape[2], wout=ref.shape[3], bias=b)
+    assert_close(y, _ref_out(ref), TOL, "conv3x3 s2 asym=%s %s" % (asym, (B, H, W, C)))
+
+
+def test_two_source_concat_and_slices():
+    """torch.cat([x, skip], 1) -> 1x1 conv (+residual), reading channel slices and writing a channel slice."""
+    from unirestore_b200 import ops
+    B, H, W, C1, C2, N = 2, 8, 12, 128, 64, 160
+    big1 = _rand(B, H, W, C1 + 64, seed=40).to(torch.bfloat16)
+    big2 = _rand(B, H, W, C2 + 8, seed=41).to(torch.bfloat16)
+    x1, x2 = big1[..., 64:], big2[..., :C2]
+    w = _rand(N, C1 + C2, seed=42, scale=(C1 + C2) ** -0.5).to(torch.bfloat16)
+    res = _rand(B, H, W, N, seed=43).to(torch.bfloat16)
+    outbig = torch.zeros(B, H, W, N + 32, device=_dev(), dtype=torch.bfloat16)
+    ops.conv_gemm(x1, w, N, x2=x2, residual=res, out=outbig[..., 32:])
+    ref = bf16_round(F.linear(torch.cat([x1, x2], -1).float(), w.float()) + res.float())
+    assert_close(outbig[..., 32:], ref, TOL, "two-source 1x1")
+    assert outbig[..., :32].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("act", ["geglu", "gate"])
+@pytest.mark.parametrize("K,N2", [(320, 2560), (128, 256), (64, 128)])
+def test_gated(act, K, N2):
+    from unirestore_b200 import ops
+    M = 200
+    x, w, b = _rand(M, K, seed=50), _rand(N2, K, seed=51, scale=K ** -0.5), _rand(N2, seed=52)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    bn = ops.pick_bn(N2, True)
+    wp, bp = ops.pack_gated_weight(wb, b, bn)
+    y = ops.conv_gemm(xb, wp, N2, bias=bp, act=ops.UR_ACT_GEGLU if act == "geglu" else ops.UR_ACT_GATE, bn=bn)
+    a, g = F.linear(xb.float(), wb.float(), b).chunk(2, -1)
+    ref = bf16_round(a * F.gelu(g) if act == "geglu" else a * g)
+    assert_close(y, ref, TOL, "gated %s" % act)
+
+
+@pytest.mark.parametrize("C,G", [(256, 4), (512, 4), (128, 2)])
+def test_grouped_conv3x3(C, G):
+    from unirestore_b200 import ops
+    B, H, W = 2, 12, 16
+    x = _rand(B, C, H, W, seed=60)
+    w = _rand(C, C // G, 3, 3, seed=61, scale=(9 * C // G) ** -0.5)
+    b = _rand(C, seed=62)
+    xb, wb = _nhwc(x), w.to(torch.bfloat16)
+    y = ops.conv_gemm(xb, ops.pack_conv_weight(wb), C, taps=ops.TAPS_3x3, bias=b, group_kc=C // G, group_nc=C // G,
+                      bn=min(128, C // G))
+    ref = _ref_out(F.conv2d(xb.float().permute(0, 3, 1, 2), wb.float(), b, padding=1, groups=G))
+    assert_close(y, ref, TOL, "grouped conv C=%d G=%d" % (C, G))
+
+
+def test_batched_gemm():
+    from unirestore_b200 import ops
+    Bt, M, K, N = 3, 200, 512, 256
+    a = _rand(Bt, M, K, seed=70).to(torch.bfloat16)
+    w = _rand(Bt, N, K, seed=71, scale=K ** -0.5).to(torch.bfloat16)
+    y = ops.conv_gemm(a, w, N, w_batched=True, alpha=0.5, out_dtype=torch.float32)
+    ref = 0.5 * torch.einsum("bmk,bnk->bmn", a.float(), w.float())
+    assert_close(y, ref, 1e-5, "batched gemm")
+
+
+def test_subpixel_phase_output_view():
+    """Strided output view (full[:, py::2, px::2]) used by the nearest-x2 upsample convolution."""
+    from unirestore_b200 import ops
+    B, H, W, C = 1, 8, 8, 64
+    xb = _rand(B, H, W, C, seed=80).to(torch.bfloat16)
+    w = _rand(C, C, seed=81, scale=C ** -0.5).to(torch.bfloat16)
+    full = torch.zeros(B, 2 * H, 2 * W, C, device=_dev(), dtype=torch.bfloat16)
+    ops.conv_gemm(xb, w, C, out=full[:, 1::2, 0::2])
+    ref = bf16_round(F.linear(xb.float(), w.float()))
+    assert_close(full[:, 1::2, 0::2], ref, TOL, "phase view")
+    assert full[:, 0::2].abs().max().item() == 0.0

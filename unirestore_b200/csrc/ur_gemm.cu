@@ -1,0 +1,429 @@
+// ur_conv_gemm: implicit-GEMM convolution / linear layer on the 5th-gen tensor cores.
+//
+//   D[128 pixels, BN channels] (fp32, TMEM) += A[128, 64] (bf16 smem, TMA) * W[BN, 64]^T (bf16 smem, TMA)
+//
+// * The activation operand is NEVER im2col-materialised: for k-block (tap, c0) the producer issues one
+//   4-D tiled TMA load of the box (64 ch, Wt, Ht, Bt) at coordinates (c0, x0*s+dx, y0*s+dy, b0) of the
+//   NHWC tensor.  Out-of-image coordinates are zero-filled by the TMA unit (= conv zero padding); stride-2
+//   convolutions use the tensor map's elementStrides.  The box lands in shared memory as 128 rows of
+//   128 B with the 128-byte swizzle, which is exactly the K-major SW128 UMMA operand layout.
+// * Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread
+//   tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld -> registers -> fused epilogue -> HBM).
+// * smem ring of STAGES x (A 16 KB + W BN*128 B), full/empty mbarriers, tcgen05.commit frees slots.
+//
+// Reference arithmetic implemented: every nn.Conv2d / nn.Linear on the UniRestore hot path
+// (see include/unirestore_b200.h for the call-site list).
+#include "ur_common.cuh"
+#include "ur_host.h"
+
+namespace ur {
+
+struct GemmParams {
+  int B, Ho, Wo, N;
+  int cblocks;         // 64-channel blocks per tap
+  int c1;              // channels of source 1 (k-blocks with c >= c1 read source 2)
+  int kc;              // K extent per tap in the packed weights
+  int ntaps, stride;
+  unsigned long long dy_pack, dx_pack;  // 4 bits per tap, value+8
+  int wt_log2, ht_log2;                 // M tile = Wt x Ht x Bt pixels, Wt*Ht*Bt = 128
+  int tiles_x, tiles_y;
+  int group_kc, group_nc;
+  int w_batched;
+  void* out;
+  int out_f32;
+  long long out_sb, out_sy, out_sx;
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  long long rowvec_sb;
+  const float* chscale;
+  long long chscale_sb;
+  const bf16* residual;
+  long long res_sb, res_sy, res_sx;
+  int act;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+
+template <int BN>
+__host__ __device__ constexpr int tmem_cols() {
+  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+}
+
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB)
+conv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap mapA1,
+                 const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW) {
+  constexpr int kWBytes = BN * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kWBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* accum_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int n0 = blockIdx.x * BN;
+  int mt = blockIdx.y;
+  const int tx = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  const int ty = mt % p.tiles_y;
+  const int tb = mt / p.tiles_y;
+  const int Wt = 1 << p.wt_log2, Ht = 1 << p.ht_log2;
+  const int Bt = kBlockM >> (p.wt_log2 + p.ht_log2);
+  const int x0 = tx * Wt, y0 = ty * Ht, b0 = tb * Bt;
+  const int nkb = p.ntaps * p.cblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapA2);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols<BN>());
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const int cbase = p.group_kc ? (n0 / p.group_nc) * p.group_kc : 0;
+      const int wb = p.w_batched ? b0 : 0;
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], kStageBytes);
+        uint8_t* sa = smem + s * kStageBytes;
+        const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
+        const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
+        const int c = cbase + cb * kBlockK;
+        const int xi = x0 * p.stride + dx, yi = y0 * p.stride + dy;
+        if (c < p.c1)
+          tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, b0);
+        else
+          tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, b0);
+        tma_load_3d(sa + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, n0, wb);
+        if (++cb == p.cblocks) {
+          cb = 0;
+          ++tap;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * kStageBytes);
+        const uint64_t da = umma_desc_k_sw128(sa);
+        const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+          tc_mma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(accum_bar);
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;       // row of the tile = TMEM lane
+    const int xl = r & (Wt - 1);
+    const int yl = (r >> p.wt_log2) & (Ht - 1);
+    const int bl = r >> (p.wt_log2 + p.ht_log2);
+    const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
+    const bool row_ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+    const bool gated = p.act == UR_ACT_GEGLU || p.act == UR_ACT_GATE;
+    const int n_out = gated ? (p.N >> 1) : p.N;
+    const int ncols = gated ? (BN >> 1) : BN;
+    const int nout0 = gated ? (n0 >> 1) : n0;
+    const long long ooff = b * p.out_sb + y * p.out_sy + x * p.out_sx;
+    const long long roff = b * p.res_sb + y * p.res_sy + x * p.res_sx;
+    const float* rowvec = p.rowvec ? p.rowvec + b * p.rowvec_sb : nullptr;
+    const float* chscale = p.chscale ? p.chscale + b * p.chscale_sb : nullptr;
+
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t va[16], vg[16];
+      tmem_ld16(trow + c, va);
+      if (gated) tmem_ld16(trow + (BN >> 1) + c, vg);
+      tmem_ld_wait();
+      const int no = nout0 + c;   // first output column of this chunk
+      if (row_ok && no < n_out) {
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int na = n0 + c + j;  // GEMM column of the `a` value (bias / rowvec index)
+        float v = __uint_as_float(va[j]) * p.alpha;
+        const bool col_ok = (no + j) < n_out;
+        if (col_ok) {
+          if (p.bias) v += __ldg(p.bias + na);
+          if (rowvec) v += __ldg(rowvec + na);
+          if (gated) {
+            const int ng = na + (BN >> 1);
+            float g = __uint_as_float(vg[j]) * p.alpha;
+            if (p.bias) g += __ldg(p.bias + ng);
+            if (rowvec) g += __ldg(rowvec + ng);
+            v = (p.act == UR_ACT_GEGLU) ? v * gelu_erf_f(g) : v * g;
+          } else if (p.act == UR_ACT_SILU) {
+            v = silu_f(v);
+          } else if (p.act == UR_ACT_GELU) {
+            v = gelu_erf_f(v);
+          }
+          if (chscale) v *= __ldg(chscale + no + j);
+        }
+        f[j] = v;
+      }
+      const bool full = (no + 16) <= n_out;
+      if (p.residual) {
+        const bf16* rp = p.residual + roff + no;
+        if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+          const uint4 r0 = *reinterpret_cast<const uint4*>(rp);
+          const uint4 r1 = *reinterpret_cast<const uint4*>(rp + 8);
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a, bb;
+            unpack_bf16(rr[j], a, bb);
+            f[2 * j] += a;
+            f[2 * j + 1] += bb;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (no + j < n_out) f[j] += __bfloat162float(rp[j]);
+        }
+      }
+      if (p.out_f32) {
+        float* op = reinterpret_cast<float*>(p.out) + ooff + no;
+        if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<float4*>(op)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (no + j < n_out) op[j] = f[j];
+        }
+      } else {
+        bf16* op = reinterpret_cast<bf16*>(p.out) + ooff + no;
+        if (full && ((reinterpret_cast<uintptr_t>(op) & 15) == 0)) {
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]);
+          o0.y = pack_bf16(f[2], f[3]);
+          o0.z = pack_bf16(f[4], f[5]);
+          o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]);
+          o1.y = pack_bf16(f[10], f[11]);
+          o1.z = pack_bf16(f[12], f[13]);
+          o1.w = pack_bf16(f[14], f[15]);
+          reinterpret_cast<uint4*>(op)[0] = o0;
+          reinterpret_cast<uint4*>(op)[1] = o1;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (no + j < n_out) op[j] = __float2bfloat16(f[j]);
+        }
+      }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols<BN>());
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+template <int BN, int STAGES, int MINB>
+static int launch_conv_gemm(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
+                            dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (kABytes + BN * kBlockK * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm)");
+    configured = true;
+  }
+  conv_gemm_kernel<BN, STAGES, MINB><<<grid, 192, smem, stream>>>(p, a1, a2, w);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error(e, "conv_gemm launch");
+  return UR_OK;
+}
+
+
+}  // namespace ur
+
+using namespace ur;
+
+extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
+  if (gated) {
+    if (n % 160 == 0) return 160;
+    if (n % 128 == 0) return 128;
+    return n % 64 == 0 ? 64 : 0;
+  }
+  if (n % 160 == 0) return 160;
+  if (n % 256 == 0 && n >= 1024) return 256;
+  if (n % 128 == 0) return 128;
+  if (n <= 64) return 64;
+  if (n % 64 == 0 && n < 256) return 64;
+  return 128;
+}
+
+extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!d || !d->x1 || !d->w || !d->out) return set_error(UR_ERR_ARG, "ur_conv_gemm: null pointer");
+  const int ctot = d->c1 + d->c2;
+  if (d->c1 <= 0 || d->c1 % 8 || d->c2 % 8 || d->ld1 % 8 || (d->c2 && (d->ld2 % 8 || !d->x2)))
+    return set_error(UR_ERR_ARG, "ur_conv_gemm: channel counts / pitches must be multiples of 8");
+  if (d->c2 > 0 && d->c1 % 64) return set_error(UR_ERR_ARG, "ur_conv_gemm: c1 %% 64 != 0 with two sources");
+  if (d->ntaps < 1 || d->ntaps > 9 || (d->stride != 1 && d->stride != 2))
+    return set_error(UR_ERR_ARG, "ur_conv_gemm: bad ntaps / stride");
+  if (d->n <= 0 || d->n % 8) return set_error(UR_ERR_ARG, "ur_conv_gemm: n must be a positive multiple of 8");
+  const bool gated = d->act == UR_ACT_GEGLU || d->act == UR_ACT_GATE;
+  int bn = d->bn ? d->bn : ur_conv_gemm_pick_bn(d->n, gated);
+  if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
+  if (gated && (d->n % bn)) return set_error(UR_ERR_ARG, "ur_conv_gemm: gated act needs n %% bn == 0");
+  int kc = ctot;
+  if (d->group_kc) {
+    if (d->group_kc % 64 || d->group_nc % bn || d->c2)
+      return set_error(UR_ERR_ARG, "ur_conv_gemm: grouped conv needs group_kc %% 64 == 0, group_nc %% bn == 0");
+    kc = d->group_kc;
+  }
+  if ((reinterpret_cast<uintptr_t>(d->x1) | reinterpret_cast<uintptr_t>(d->x2) | reinterpret_cast<uintptr_t>(d->w)) & 15)
+    return set_error(UR_ERR_ARG, "ur_conv_gemm: pointers must be 16-byte aligned");
+
+  // ---- M tile shape: minimise padded work, prefer wide tiles
+  int best_w = 0, best_h = 0;
+  long long best_cost = -1;
+  for (int wl = 7; wl >= 0; --wl) {
+    for (int hl = 0; wl + hl <= 7; ++hl) {
+      const int Wt = 1 << wl, Ht = 1 << hl, Bt = 128 >> (wl + hl);
+      if (d->w_batched && Bt != 1) continue;
+      const long long tiles = 1LL * ((d->wout + Wt - 1) / Wt) * ((d->hout + Ht - 1) / Ht) * ((d->batch + Bt - 1) / Bt);
+      if (best_cost < 0 || tiles < best_cost) {
+        best_cost = tiles;
+        best_w = wl;
+        best_h = hl;
+      }
+    }
+  }
+  if (best_cost < 0) return set_error(UR_ERR_ARG, "ur_conv_gemm: no tile shape");
+  const int Wt = 1 << best_w, Ht = 1 << best_h, Bt = 128 >> (best_w + best_h);
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->batch;
+  p.Ho = d->hout;
+  p.Wo = d->wout;
+  p.N = d->n;
+  p.cblocks = (kc + 63) / 64;
+  p.c1 = d->group_kc ? (1 << 30) : d->c1;
+  p.kc = kc;
+  p.ntaps = d->ntaps;
+  p.stride = d->stride;
+  for (int t = 0; t < d->ntaps; ++t) {
+    if (d->tap_dy[t] < -8 || d->tap_dy[t] > 7 || d->tap_dx[t] < -8 || d->tap_dx[t] > 7)
+      return set_error(UR_ERR_ARG, "ur_conv_gemm: tap offset out of range");
+    p.dy_pack |= static_cast<unsigned long long>(d->tap_dy[t] + 8) << (4 * t);
+    p.dx_pack |= static_cast<unsigned long long>(d->tap_dx[t] + 8) << (4 * t);
+  }
+  p.wt_log2 = best_w;
+  p.ht_log2 = best_h;
+  p.tiles_x = (d->wout + Wt - 1) / Wt;
+  p.tiles_y = (d->hout + Ht - 1) / Ht;
+  const int tiles_b = (d->batch + Bt - 1) / Bt;
+  p.group_kc = d->group_kc;
+  p.group_nc = d->group_nc;
+  p.w_batched = d->w_batched;
+  p.out = d->out;
+  p.out_f32 = d->out_dtype == UR_DT_F32;
+  p.out_sb = d->out_sb;
+  p.out_sy = d->out_sy;
+  p.out_sx = d->out_sx;
+  p.alpha = d->alpha;
+  p.bias = d->bias;
+  p.rowvec = d->rowvec;
+  p.rowvec_sb = d->rowvec_sb;
+  p.chscale = d->chscale;
+  p.chscale_sb = d->chscale_sb;
+  p.residual = static_cast<const bf16*>(d->residual);
+  p.res_sb = d->res_sb;
+  p.res_sy = d->res_sy;
+  p.res_sx = d->res_sx;
+  p.act = d->act;
+
+  // ---- tensor maps
+  CUtensorMap mA1, mA2, mW;
+  const uint32_t s = static_cast<uint32_t>(d->stride);
+  const uint32_t boxA[4] = {64u, static_cast<uint32_t>(Wt) * s, static_cast<uint32_t>(Ht) * s, static_cast<uint32_t>(Bt)};
+  const uint32_t estrA[4] = {1u, s, s, 1u};
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->c1), static_cast<uint64_t>(d->win), static_cast<uint64_t>(d->hin),
+                              static_cast<uint64_t>(d->batch)};
+    const uint64_t str[3] = {static_cast<uint64_t>(d->ld1) * 2, static_cast<uint64_t>(d->ld1) * 2 * d->win,
+                             static_cast<uint64_t>(d->ld1) * 2 * d->win * d->hin};
+    int rc = encode_tensor_map(&mA1, const_cast<void*>(d->x1), 4, dims, str, boxA, estrA);
+    if (rc) return rc;
+  }
+  if (d->c2 > 0) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(d->c2), static_cast<uint64_t>(d->win), static_cast<uint64_t>(d->hin),
+                              static_cast<uint64_t>(d->batch)};
+    const uint64_t str[3] = {static_cast<uint64_t>(d->ld2) * 2, static_cast<uint64_t>(d->ld2) * 2 * d->win,
+                             static_cast<uint64_t>(d->ld2) * 2 * d->win * d->hin};
+    int rc = encode_tensor_map(&mA2, const_cast<void*>(d->x2), 4, dims, str, boxA, estrA);
+    if (rc) return rc;
+  } else {
+    mA2 = mA1;
+  }
+  {
+    const uint64_t ktot = static_cast<uint64_t>(d->ntaps) * kc;
+    const uint64_t dims[3] = {ktot, static_cast<uint64_t>(d->n), static_cast<uint64_t>(d->w_batched ? d->batch : 1)};
+    const uint64_t str[2] = {ktot * 2, ktot * 2 * d->n};
+    const uint32_t box[3] = {64u, static_cast<uint32_t>(bn), 1u};
+    const uint32_t estr[3] = {1u, 1u, 1u};
+    int rc = encode_tensor_map(&mW, const_cast<void*>(d->w), 3, dims, str, box, estr);
+    if (rc) return rc;
+  }
+
+  dim3 grid((d->n + bn - 1) / bn, p.tiles_x * p.tiles_y * tiles_b, 1);
+  if (grid.y > 65535) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many M tiles");
+  switch (bn) {
+    case 64: return launch_conv_gemm<64, 4, 2>(p, mA1, mA2, mW, grid, stream);
+    case 128: return launch_conv_gemm<128, 3, 2>(p, mA1, mA2, mW, grid, stream);
+    case 160: return launch_conv_gemm<160, 3, 2>(p, mA1, mA2, mW, grid, stream);
+    default: return launch_conv_gemm<256, 4, 1>(p, mA1, mA2, mW, grid, stream);
+  }
+}
