@@ -65,6 +65,8 @@ typedef struct ur_conv_desc {
   int batch, hin, win; /* input extent */
   const void* w;       /* bf16 [n, ntaps*kc] (K contiguous); kc = c1+c2, or group_kc for grouped conv */
   int w_batched;       /* 1: w has a leading [batch] dimension (batched GEMM, tile never spans images) */
+  int64_t w_ld;        /* row pitch of w in elements (0 = dense: ntaps*kc) */
+  int64_t w_bs;        /* batch stride of w in elements (0 = dense: n*w_ld) */
   int n;               /* GEMM N (= output channels; gated acts store n/2 channels) */
   int ntaps;           /* 1..9 */
   int tap_dy[9];
@@ -91,6 +93,80 @@ typedef struct ur_conv_desc {
 int ur_conv_gemm(const ur_conv_desc* desc_host, void* stream);
 /* N tile the auto heuristic picks for (n, m_tiles); weight packers for gated acts must use it. */
 int ur_conv_gemm_pick_bn(int n, int gated);
+
+/* ------------------------------------------------------------------------------------------------
+ * Normalisation (HBM-bound, bf16 channels-last, 128-bit vectorised)
+ * stats layout: double [batch][stats_ld channels][2] = (sum, sum of squares) over the pixels of one image.
+ * ---------------------------------------------------------------------------------------------- */
+/* Per-(image, channel) sums: first half of nn.GroupNorm (diffusers ResnetBlock2D.norm1/norm2, Attention.group_norm,
+ * Transformer2DModel.norm, conv_norm_out; AdaNAFV2.group_norm cfrm.py:19), nn.InstanceNorm2d (taskeditor.py:31,40,49)
+ * and nn.AdaptiveAvgPool2d(1) (nafnet_arch.py:62, cfrm.py:24,30, taskeditor.py:35,44,53). */
+int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int batch, int pixels, int channels, double* stats,
+                  int stats_ld, int stats_off, int zero_first, void* stream);
+/* out = [silu]( (cat(x1,x2) - mean_g) * rstd_g * gamma + beta ), group statistics from ur_chan_stats. */
+int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2, int64_t is2, int c2,
+                  const double* stats, int groups, int batch, int pixels, const float* gamma, const float* beta,
+                  float eps, int silu, void* out, int64_t ldo, int64_t iso, void* stream);
+/* nn.LayerNorm over the channel dim of every token (BasicTransformerBlock.norm1-3; timm LayerNorm2d nafnet_arch.py:97-98). */
+int ur_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int channels, const float* gamma,
+                 const float* beta, float eps, void* stream);
+/* x[b,p,c] *= scale[b,c] in place (nafnet_arch.py:122 `x * self.sca(x)`; cfrm.py:49-52). */
+int ur_scale_channels(void* x, int64_t ld, int64_t img_stride, int batch, int pixels, int channels, const float* scale,
+                      int scale_ld, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Attention helpers (unfused path: S = QK^T by ur_conv_gemm, softmax here, O = P V by ur_conv_gemm)
+ * diffusers Attention / F.scaled_dot_product_attention (controller.py:183-185, VAE mid block, base_model.py:138).
+ * ---------------------------------------------------------------------------------------------- */
+int ur_softmax_rows(const float* scores, int64_t ld_s, void* probs, int64_t ld_p, int64_t rows, int n_valid, int n_pad,
+                    void* stream);
+int ur_transpose_tokens(const void* x, int64_t ld, int64_t batch_stride, int batch, int tokens, int dim, void* out,
+                        int tokens_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CFRM / TFA specific small kernels
+ * ---------------------------------------------------------------------------------------------- */
+/* NAFBlock: y = SimpleGate(dwconv3x3(x)) and GAP sums of y (nafnet_arch.py:41-49,62,115-122). weight fp32 [2c,9]. */
+int ur_dwconv3x3_gate(const void* x, int batch, int h, int w, int c, const float* weight, const float* bias, void* y,
+                      double* stats, void* stream);
+/* y[b,n] = act_out(W[n,:] . act_in(x[b, group(n)*k : +k]) + bias[n]); acts: 0 none 1 silu 2 gelu 3 tanh.
+ * in_mode 1: x is a ur_chan_stats array and the input is sum*in_scale (pooled mean).
+ * TimestepEmbedding / time_emb_proj (base_model.py:104-106, controller.py:196-197), NAFBlock.sca (nafnet_arch.py:61-65). */
+int ur_small_linear(const void* x, int in_mode, float in_scale, int64_t x_ld, const float* w, const float* bias,
+                    float* y, int64_t y_ld, int batch, int n, int k, int groups, int act_in, int act_out, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[b] = [cos(t f), sin(t f)]. */
+int ur_timestep_embedding(const int64_t* timesteps, int batch, int dim, float* out, void* stream);
+/* AdaNAFV2 intra-/inter-group attention -> scale[b, 4c] (cfrm.py:22-34,47-52). */
+int ur_adanaf_scales(const double* stats, int pixels, int batch, int c4, int groups, const float* w_intra,
+                     const float* b_intra, const float* w_inter, const float* b_inter, float* scale, void* stream);
+/* TaskFeatureAdapter prompt update (taskeditor.py:78-106): pooled gate branches -> o [B,D], cond_next [B,T,D/2]. */
+int ur_tfa_gates(const double* stats, int pixels, int batch, int prompt_len, int dim, const float* cond,
+                 const float* w_out, const float* b_out, const float* w_pt, const float* b_pt, float* o,
+                 float* cond_next, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Latent-space elementwise (fp32 NCHW latents [B,4,h,w]; *_nhwc8 = bf16 channels-last copy padded to 8 ch)
+ * ---------------------------------------------------------------------------------------------- */
+/* z = (mean + exp(0.5*clamp(logvar,-30,20)) * noise) * scaling_factor (autoencoder.py:152-155). */
+int ur_posterior_sample(const float* moments, const float* noise, float scaling_factor, int batch, int hw, float* z,
+                        void* z_nhwc8, void* stream);
+/* out = a*x + b*y (DDPMScheduler.add_noise, unifie.py:88); out_nhwc8 = bf16(scale8 * out) (autoencoder.py:170). */
+int ur_latent_axpby(const float* x, float a, const float* y, float b, int batch, int hw, float* out, void* out_nhwc8,
+                    float scale8, void* stream);
+/* DDIMScheduler.step, eta = 0 (unifie.py:150), in place on x. */
+int ur_ddim_step(float* x, const float* eps, int ld_eps, float sqrt_alpha_t, float sqrt_one_minus_alpha_t,
+                 float sqrt_alpha_prev, float sqrt_one_minus_alpha_prev, int clip_sample, int batch, int hw,
+                 void* x_nhwc8, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image layout (fp32 NCHW images <-> channels-last)
+ * ---------------------------------------------------------------------------------------------- */
+/* out bf16 [B,H,W,8] = a*img + b for the first `channels`, zeros after (autoencoder.py:151 `x*2-1`). */
+int ur_image_to_nhwc8(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels, int h,
+                      int w, float a, float b, void* out, void* stream);
+/* out fp32 [B,C,h,w] = a*src[:, :h, :w, :C] + b (autoencoder.py:175 `(x+1)/2`, crop of unifie.py:164). */
+int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w, float a, float b,
+                     float* out, void* stream);
 
 #ifdef __cplusplus
 }

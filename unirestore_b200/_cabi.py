@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
         ("x1", C.c_void_p), ("x2", C.c_void_p),
         ("c1", C.c_int), ("c2", C.c_int), ("ld1", C.c_int), ("ld2", C.c_int),
         ("batch", C.c_int), ("hin", C.c_int), ("win", C.c_int),
-        ("w", C.c_void_p), ("w_batched", C.c_int), ("n", C.c_int),
+        ("w", C.c_void_p), ("w_batched", C.c_int), ("w_ld", C.c_int64), ("w_bs", C.c_int64), ("n", C.c_int),
         ("ntaps", C.c_int), ("tap_dy", C.c_int * 9), ("tap_dx", C.c_int * 9), ("stride", C.c_int),
         ("group_kc", C.c_int), ("group_nc", C.c_int),
         ("hout", C.c_int), ("wout", C.c_int),
@@ -40,6 +40,8 @@ class ConvDesc(C.Structure):
     ]
 
 
+_P, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
 # name -> (restype, argtypes); every symbol include/unirestore_b200.h declares
 SIGNATURES = {
     "ur_init": (C.c_int, [C.c_int]),
@@ -47,6 +49,23 @@ SIGNATURES = {
     "ur_version": (C.c_int, []),
     "ur_conv_gemm": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "ur_conv_gemm_pick_bn": (C.c_int, [C.c_int, C.c_int]),
+    "ur_chan_stats": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "ur_norm_apply": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _I64,
+                                _I64, _P]),
+    "ur_layernorm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P]),
+    "ur_scale_channels": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _P]),
+    "ur_softmax_rows": (C.c_int, [_P, _I64, _P, _I64, _I64, _I, _I, _P]),
+    "ur_transpose_tokens": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _P]),
+    "ur_dwconv3x3_gate": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "ur_small_linear": (C.c_int, [_P, _I, _F, _I64, _P, _P, _P, _I64, _I, _I, _I, _I, _I, _I, _P]),
+    "ur_timestep_embedding": (C.c_int, [_P, _I, _I, _P, _P]),
+    "ur_adanaf_scales": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "ur_tfa_gates": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ur_posterior_sample": (C.c_int, [_P, _P, _F, _I, _I, _P, _P, _P]),
+    "ur_latent_axpby": (C.c_int, [_P, _F, _P, _F, _I, _I, _P, _P, _F, _P]),
+    "ur_ddim_step": (C.c_int, [_P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P]),
+    "ur_image_to_nhwc8": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "ur_nhwc_to_image": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P]),
 }
 
 _lib = None

@@ -311,7 +311,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   if (d->c2 > 0 && d->c1 % 64) return set_error(UR_ERR_ARG, "ur_conv_gemm: c1 %% 64 != 0 with two sources");
   if (d->ntaps < 1 || d->ntaps > 9 || (d->stride != 1 && d->stride != 2))
     return set_error(UR_ERR_ARG, "ur_conv_gemm: bad ntaps / stride");
-  if (d->n <= 0 || d->n % 8) return set_error(UR_ERR_ARG, "ur_conv_gemm: n must be a positive multiple of 8");
+  if (d->n <= 0) return set_error(UR_ERR_ARG, "ur_conv_gemm: n must be positive");
   const bool gated = d->act == UR_ACT_GEGLU || d->act == UR_ACT_GATE;
   int bn = d->bn ? d->bn : ur_conv_gemm_pick_bn(d->n, gated);
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
@@ -411,7 +411,10 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   {
     const uint64_t ktot = static_cast<uint64_t>(d->ntaps) * kc;
     const uint64_t dims[3] = {ktot, static_cast<uint64_t>(d->n), static_cast<uint64_t>(d->w_batched ? d->batch : 1)};
-    const uint64_t str[2] = {ktot * 2, ktot * 2 * d->n};
+    const uint64_t wld = d->w_ld ? static_cast<uint64_t>(d->w_ld) : ktot;
+    const uint64_t wbs = d->w_bs ? static_cast<uint64_t>(d->w_bs) : wld * d->n;
+    if (wld % 8 || wbs % 8) return set_error(UR_ERR_ARG, "ur_conv_gemm: weight pitches must be multiples of 8");
+    const uint64_t str[2] = {wld * 2, wbs * 2};
     const uint32_t box[3] = {64u, static_cast<uint32_t>(bn), 1u};
     const uint32_t estr[3] = {1u, 1u, 1u};
     int rc = encode_tensor_map(&mW, const_cast<void*>(d->w), 3, dims, str, box, estr);

@@ -1,0 +1,524 @@
+// Small / HBM-bound kernels around the GEMM and attention kernels:
+//   ur_softmax_rows        fp32 scores -> bf16 probabilities (unfused attention for head_dim 512)
+//   ur_transpose_tokens    [B, T, d] -> [B, d, Tpad] (V^T operand of the P*V GEMM)
+//   ur_dwconv3x3_gate      depthwise 3x3 + SimpleGate + global-average-pool sums (NAFBlock)
+//   ur_small_linear        tiny fp32 (grouped) linear on pooled / embedding vectors
+//   ur_timestep_embedding  sinusoidal timestep features (diffusers Timesteps)
+//   ur_adanaf_scales       AdaNAFV2 intra / inter group attention -> per-(image, channel) scale
+//   ur_tfa_gates           TaskFeatureAdapter prompt update (softmax gates, out gate, prompt_trans)
+//   ur_posterior_sample / ur_add_noise / ur_ddim_step / ur_latent_to_nhwc8   latent-space elementwise
+//   ur_image_to_nhwc8 / ur_nhwc8_to_image   fp32 NCHW images <-> bf16 channels-last (8-channel padded)
+#include "ur_common.cuh"
+#include "ur_host.h"
+
+namespace ur {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ float block_reduce(float v, bool is_max, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = is_max ? -INFINITY : 0.f;
+  for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, sh[i]) : r + sh[i];
+  return r;
+}
+
+// ------------------------------------------------------------------------------------ softmax_rows
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, bf16* __restrict__ p, long long ldp,
+                                    int n_valid, int n_pad) {
+  __shared__ float sh[32];
+  const long long row = blockIdx.x;
+  const float* sr = s + row * lds;
+  bf16* pr = p + row * ldp;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < n_valid; i += blockDim.x) m = fmaxf(m, sr[i]);
+  m = block_reduce(m, true, sh);
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n_valid; i += blockDim.x) sum += __expf(sr[i] - m);
+  sum = block_reduce(sum, false, sh);
+  const float inv = 1.f / sum;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x)
+    pr[i] = __float2bfloat16(i < n_valid ? __expf(sr[i] - m) * inv : 0.f);
+}
+
+// ------------------------------------------------------------------------------------ transpose_tokens
+__global__ void transpose_tokens_kernel(const bf16* __restrict__ x, long long ld, long long bs, int T, int D,
+                                        bf16* __restrict__ out, int Tpad) {
+  __shared__ bf16 tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, d = d0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && d < D) ? x[b * bs + t * ld + d] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int d = d0 + i, t = t0 + threadIdx.x;
+    if (d < D && t < Tpad) out[(static_cast<long long>(b) * D + d) * Tpad + t] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------ dwconv3x3_gate
+// x [B,H,W,2c] -> y [B,H,W,c] = dw3x3(x)[..., :c] * dw3x3(x)[..., c:]   (nafnet_arch.py:41-49,115-118)
+// plus per-(image, channel) sums of y for the SCA global average pool (nafnet_arch.py:62).
+__global__ void dwconv3x3_gate_kernel(const bf16* __restrict__ x, int H, int W, int c, const float* __restrict__ wgt,
+                                      const float* __restrict__ bias, bf16* __restrict__ y, double* __restrict__ stats,
+                                      int CV, int PL, int chunk) {
+  extern __shared__ float sh[];  // pooled[c]
+  const int b = blockIdx.y;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int C2 = 2 * c;
+  const int P = H * W;
+  const int p0 = blockIdx.x * chunk, p1 = min(P, p0 + chunk);
+  const bf16* xb = x + static_cast<long long>(b) * P * C2;
+  float pool[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pool[j] = 0.f;
+  for (int p = p0 + pl; p < p1; p += PL) {
+    const int py = p / W, px = p % W;
+    float a[8], g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] = __ldg(bias + cv * 8 + j);
+      g[j] = __ldg(bias + c + cv * 8 + j);
+    }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = py + ky - 1;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const bf16* src = xb + (static_cast<long long>(yy) * W + xx) * C2 + cv * 8;
+        const uint4 va = __ldg(reinterpret_cast<const uint4*>(src));
+        const uint4 vg = __ldg(reinterpret_cast<const uint4*>(src + c));
+        const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ug[4] = {vg.x, vg.y, vg.z, vg.w};
+        const int t = ky * 3 + kx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f0, f1;
+          unpack_bf16(ua[j], f0, f1);
+          a[2 * j] += f0 * __ldg(wgt + (cv * 8 + 2 * j) * 9 + t);
+          a[2 * j + 1] += f1 * __ldg(wgt + (cv * 8 + 2 * j + 1) * 9 + t);
+          unpack_bf16(ug[j], f0, f1);
+          g[2 * j] += f0 * __ldg(wgt + (c + cv * 8 + 2 * j) * 9 + t);
+          g[2 * j + 1] += f1 * __ldg(wgt + (c + cv * 8 + 2 * j + 1) * 9 + t);
+        }
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float r0 = a[2 * j] * g[2 * j];
+      const float r1 = a[2 * j + 1] * g[2 * j + 1];
+      o[j] = pack_bf16(r0, r1);
+      float q0, q1;
+      unpack_bf16(o[j], q0, q1);
+      pool[2 * j] += q0;
+      pool[2 * j + 1] += q1;
+    }
+    *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * P + p) * c + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], pool[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x)
+    atomicAdd(stats + (static_cast<long long>(b) * c + i) * 2, static_cast<double>(sh[i]));
+}
+
+// ------------------------------------------------------------------------------------ small_linear
+// y[b, n] = act_out( sum_k W[n, k] * act_in(x[b, g*kg + k]) + bias[n] ),  one warp per (b, n).
+// in_mode 1: x is the fp64 (sum, sumsq) statistics array and the input value is sum * in_scale.
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == 1) return silu_f(v);
+  if (act == 2) return gelu_erf_f(v);
+  if (act == 3) return tanhf(v);
+  return v;
+}
+__global__ void small_linear_kernel(const void* __restrict__ x, int in_mode, float in_scale, long long x_ld,
+                                    const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
+                                    long long y_ld, int B, int N, int K, int groups, int act_in, int act_out) {
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= static_cast<long long>(B) * N) return;
+  const int b = static_cast<int>(gw / N), n = static_cast<int>(gw % N);
+  const int ng = N / groups;
+  const int koff = (n / ng) * K;
+  const float* wr = w + static_cast<long long>(n) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv;
+    if (in_mode == 1)
+      xv = static_cast<float>(static_cast<const double*>(x)[(b * x_ld + koff + k) * 2] * static_cast<double>(in_scale));
+    else
+      xv = static_cast<const float*>(x)[b * x_ld + koff + k];
+    acc += __ldg(wr + k) * apply_act(xv, act_in);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) y[b * y_ld + n] = apply_act(acc + (bias ? bias[n] : 0.f), act_out);
+}
+
+// ------------------------------------------------------------------------------------ timestep embedding
+// diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i), sin(t f_i)],
+// f_i = exp(-ln(10000) * i / half)   (base_model.py:104, controller.py:86,196)
+__global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, j = i % half;
+  const float freq = expf(-logf(10000.f) * static_cast<float>(j) / static_cast<float>(half));
+  const float arg = static_cast<float>(t[b]) * freq;
+  out[b * dim + j] = cosf(arg);
+  out[b * dim + half + j] = sinf(arg);
+}
+
+// ------------------------------------------------------------------------------------ adanaf_scales
+// cfrm.py:22-34,47-52: x = x * intra(GAP(x)); x = x * inter(GAP(x)) per group.  With m = GAP(gelu(conv)) this is
+// scale[ch] = intra[ch] * inter[group(ch)],  intra = Wi (grouped 1x1) m + bi,  inter = Wg (m * intra) + bg.
+__global__ void adanaf_scales_kernel(const double* __restrict__ stats, float inv_p, int C4, int G,
+                                     const float* __restrict__ wi, const float* __restrict__ bi,
+                                     const float* __restrict__ wg, const float* __restrict__ bg,
+                                     float* __restrict__ scale) {
+  extern __shared__ float sh[];  // m[C4], intra[C4], inter[G]
+  float* m = sh;
+  float* intra = sh + C4;
+  float* inter = sh + 2 * C4;
+  const int b = blockIdx.x;
+  const int kg = C4 / G;
+  for (int c = threadIdx.x; c < C4; c += blockDim.x)
+    m[c] = static_cast<float>(stats[(static_cast<long long>(b) * C4 + c) * 2] * static_cast<double>(inv_p));
+  __syncthreads();
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+    const int g = c / kg;
+    float acc = bi[c];
+    for (int k = 0; k < kg; ++k) acc += wi[c * kg + k] * m[g * kg + k];
+    intra[c] = acc;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int g = warp; g < G; g += nw) {
+    float acc = 0.f;
+    for (int c = lane; c < C4; c += 32) acc += wg[g * C4 + c] * (m[c] * intra[c]);
+    acc = warp_sum(acc);
+    if (lane == 0) inter[g] = acc + bg[g];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) scale[static_cast<long long>(b) * C4 + c] = intra[c] * inter[c / kg];
+}
+
+// ------------------------------------------------------------------------------------ tfa_gates
+// taskeditor.py:78-106.  pooled = GAP of the three gate branches, channel layout [filter | info | content] x (T*D).
+__global__ void tfa_gates_kernel(const double* __restrict__ stats, float inv_p, int T, int D,
+                                 const float* __restrict__ cond, const float* __restrict__ w_out,
+                                 const float* __restrict__ b_out, const float* __restrict__ w_pt,
+                                 const float* __restrict__ b_pt, float* __restrict__ o, float* __restrict__ cond_next) {
+  extern __shared__ float sh[];  // pooled[3*T*D], newc[T*D], red[32]
+  const int hid = T * D;
+  float* pooled = sh;
+  float* newc = sh + 3 * hid;
+  float* red = newc + hid;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < 3 * hid; i += blockDim.x)
+    pooled[i] = static_cast<float>(stats[(static_cast<long long>(b) * 3 * hid + i) * 2] * static_cast<double>(inv_p));
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    float* f = pooled + t * D;
+    float* ig = pooled + hid + t * D;
+    float mf = -INFINITY, mi = -INFINITY;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      mf = fmaxf(mf, f[d]);
+      mi = fmaxf(mi, ig[d]);
+    }
+    mf = block_reduce(mf, true, red);
+    mi = block_reduce(mi, true, red);
+    float sf = 0.f, si = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      sf += expf(f[d] - mf);
+      si += expf(ig[d] - mi);
+    }
+    sf = block_reduce(sf, false, red);
+    si = block_reduce(si, false, red);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      const float fv = expf(f[d] - mf) / sf, iv = expf(ig[d] - mi) / si;
+      const float cv = tanhf(pooled[2 * hid + t * D + d]);
+      newc[t * D + d] = fv * cond[(static_cast<long long>(b) * T + t) * D + d] + iv * cv;
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int n = warp; n < D; n += nw) {  // out_gate: Linear(T*D -> D) + tanh
+    float acc = 0.f;
+    for (int k = lane; k < hid; k += 32) acc += w_out[static_cast<long long>(n) * hid + k] * newc[k];
+    acc = warp_sum(acc);
+    if (lane == 0) o[static_cast<long long>(b) * D + n] = tanhf(acc + b_out[n]);
+  }
+  if (w_pt) {  // prompt_trans: Linear(D -> D/2) + GELU per prompt token
+    const int Dh = D / 2;
+    for (int idx = warp; idx < T * Dh; idx += nw) {
+      const int t = idx / Dh, n = idx % Dh;
+      float acc = 0.f;
+      for (int k = lane; k < D; k += 32) acc += w_pt[static_cast<long long>(n) * D + k] * newc[t * D + k];
+      acc = warp_sum(acc);
+      if (lane == 0) cond_next[(static_cast<long long>(b) * T + t) * Dh + n] = gelu_erf_f(acc + b_pt[n]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ latent kernels
+// latents are fp32 NCHW [B,4,h,w] (reference layout); *_nhwc8 is the bf16 channels-last copy padded to 8
+// channels that feeds conv_in through the GEMM kernel.
+__device__ __forceinline__ void store_nhwc8(bf16* dst, float v0, float v1, float v2, float v3) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(v0, v1), pack_bf16(v2, v3), 0u, 0u);
+}
+// autoencoder.py:152-155 (DiagonalGaussianDistribution.sample * scaling_factor); moments: fp32 [B,h,w,8] (mean|logvar)
+__global__ void posterior_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float sf,
+                                        long long hw, long long total, float* __restrict__ z, bf16* __restrict__ z8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / hw, p = i % hw;
+    const float4 mean = *reinterpret_cast<const float4*>(moments + i * 8);
+    const float4 lv = *reinterpret_cast<const float4*>(moments + i * 8 + 4);
+    const float mm[4] = {mean.x, mean.y, mean.z, mean.w}, ll[4] = {lv.x, lv.y, lv.z, lv.w};
+    float r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float sd = expf(0.5f * fminf(fmaxf(ll[c], -30.f), 20.f));
+      const long long o = (b * 4 + c) * hw + p;
+      r[c] = (mm[c] + sd * noise[o]) * sf;
+      z[o] = r[c];
+    }
+    if (z8) store_nhwc8(z8 + i * 8, r[0], r[1], r[2], r[3]);
+  }
+}
+// out = a*x + b*y on fp32 NCHW latents (y may be null) + optional bf16 NHWC8 copy of `scale8 * out`.
+// DDPMScheduler.add_noise (unifie.py:88) and the latent / scaling_factor of autoencoder.py:170.
+__global__ void latent_axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float bcoef,
+                                    long long hw, long long total, float* __restrict__ out, bf16* __restrict__ out8,
+                                    float scale8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / hw, p = i % hw;
+    float r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long o = (b * 4 + c) * hw + p;
+      float v = a * x[o];
+      if (y) v += bcoef * y[o];
+      r[c] = v;
+      if (out) out[o] = v;
+    }
+    if (out8) store_nhwc8(out8 + i * 8, r[0] * scale8, r[1] * scale8, r[2] * scale8, r[3] * scale8);
+  }
+}
+// DDIMScheduler.step, eta = 0 (unifie.py:150): x0 = (x - sqrt(1-a_t) e) / sqrt(a_t); prev = sqrt(a_p) x0 + sqrt(1-a_p) e
+// eps: fp32 [B,h,w,ld_eps] channels-last (GEMM output), x: fp32 NCHW, updated in place.
+__global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_eps, float sqrt_at,
+                                 float sqrt_1mat, float sqrt_ap, float sqrt_1map, int clip, long long hw,
+                                 long long total, bf16* __restrict__ x8) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / hw, p = i % hw;
+    float r[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long o = (b * 4 + c) * hw + p;
+      const float e = eps[i * ld_eps + c];
+      float x0 = (x[o] - sqrt_1mat * e) / sqrt_at;
+      if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+      r[c] = sqrt_ap * x0 + sqrt_1map * e;
+      x[o] = r[c];
+    }
+    if (x8) store_nhwc8(x8 + i * 8, r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ image layout kernels
+// fp32 image [B,3,H,W] (arbitrary strides) -> bf16 [B,H,W,8] = a*x + b, channels 3..7 zero  (autoencoder.py:151)
+__global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy,
+                                      long long sx, int C, int H, int W, float a, float bofs, long long total,
+                                      bf16* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(i % W);
+    const int yy = static_cast<int>((i / W) % H);
+    const long long b = i / (static_cast<long long>(W) * H);
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? a * img[b * sb + c * sc + yy * sy + xx * sx] + bofs : 0.f;
+    *reinterpret_cast<uint4*>(out + i * 8) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+// fp32 channels-last [B,Hs,Ws,ld] -> fp32 NCHW [B,C,H,W] = a*x + b over the top-left HxW crop (autoencoder.py:175,
+// unifie.py:164)
+__global__ void nhwc_to_image_kernel(const float* __restrict__ src, int ld, int Hs, int Ws, int C, int H, int W,
+                                     float a, float bofs, long long total, float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xx = static_cast<int>(i % W);
+    const int yy = static_cast<int>((i / W) % H);
+    const int c = static_cast<int>((i / (static_cast<long long>(W) * H)) % C);
+    const long long b = i / (static_cast<long long>(W) * H * C);
+    out[i] = a * src[((b * Hs + yy) * Ws + xx) * ld + c] + bofs;
+  }
+}
+
+static int grid_for(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 16LL * num_sms();
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace ur
+
+using namespace ur;
+
+#define UR_LAUNCH_CHECK(what)                                                \
+  do {                                                                       \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    return e__ == cudaSuccess ? UR_OK : set_cuda_error(e__, what " launch"); \
+  } while (0)
+
+extern "C" int ur_softmax_rows(const float* scores, int64_t ld_s, void* probs, int64_t ld_p, int64_t rows, int n_valid,
+                               int n_pad, void* stream) {
+  if (!scores || !probs || rows <= 0 || n_valid <= 0 || n_pad < n_valid)
+    return set_error(UR_ERR_ARG, "ur_softmax_rows: bad arguments");
+  const int threads = n_valid >= 1024 ? 256 : (n_valid >= 128 ? 128 : 32);
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, ld_s, static_cast<bf16*>(probs), ld_p, n_valid, n_pad);
+  UR_LAUNCH_CHECK("ur_softmax_rows");
+}
+
+extern "C" int ur_transpose_tokens(const void* x, int64_t ld, int64_t batch_stride, int batch, int tokens, int dim,
+                                   void* out, int tokens_pad, void* stream) {
+  if (!x || !out || tokens_pad < tokens) return set_error(UR_ERR_ARG, "ur_transpose_tokens: bad arguments");
+  dim3 grid((tokens_pad + 31) / 32, (dim + 31) / 32, batch);
+  transpose_tokens_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const bf16*>(x), ld, batch_stride, tokens, dim, static_cast<bf16*>(out), tokens_pad);
+  UR_LAUNCH_CHECK("ur_transpose_tokens");
+}
+
+extern "C" int ur_dwconv3x3_gate(const void* x, int batch, int h, int w, int c, const float* weight, const float* bias,
+                                 void* y, double* stats, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x || !weight || !bias || !y || !stats || c % 8 || c > 4096)
+    return set_error(UR_ERR_ARG, "ur_dwconv3x3_gate: bad arguments");
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * static_cast<size_t>(batch) * c, stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "ur_dwconv3x3_gate memset");
+  const int CV = c / 8;
+  const int PL = CV >= 256 ? 1 : 256 / CV;
+  const int P = h * w;
+  const int target = max(1, (8 * num_sms()) / batch);
+  int chunk = (P + target - 1) / target;
+  if (chunk < PL * 2) chunk = PL * 2;
+  dim3 grid((P + chunk - 1) / chunk, batch);
+  dwconv3x3_gate_kernel<<<grid, CV * PL, c * sizeof(float), stream>>>(static_cast<const bf16*>(x), h, w, c, weight, bias,
+                                                                     static_cast<bf16*>(y), stats, CV, PL, chunk);
+  UR_LAUNCH_CHECK("ur_dwconv3x3_gate");
+}
+
+extern "C" int ur_small_linear(const void* x, int in_mode, float in_scale, int64_t x_ld, const float* w,
+                               const float* bias, float* y, int64_t y_ld, int batch, int n, int k, int groups,
+                               int act_in, int act_out, void* stream) {
+  if (!x || !w || !y || groups <= 0 || n % groups) return set_error(UR_ERR_ARG, "ur_small_linear: bad arguments");
+  const long long warps = static_cast<long long>(batch) * n;
+  const int block = 256;
+  const unsigned grid = static_cast<unsigned>((warps * 32 + block - 1) / block);
+  small_linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, in_mode, in_scale, x_ld, w, bias, y, y_ld,
+                                                                            batch, n, k, groups, act_in, act_out);
+  UR_LAUNCH_CHECK("ur_small_linear");
+}
+
+extern "C" int ur_timestep_embedding(const int64_t* timesteps, int batch, int dim, float* out, void* stream) {
+  if (!timesteps || !out || dim % 2) return set_error(UR_ERR_ARG, "ur_timestep_embedding: bad arguments");
+  const int total = batch * dim / 2;
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(timesteps), batch, dim, out);
+  UR_LAUNCH_CHECK("ur_timestep_embedding");
+}
+
+extern "C" int ur_adanaf_scales(const double* stats, int pixels, int batch, int c4, int groups, const float* w_intra,
+                                const float* b_intra, const float* w_inter, const float* b_inter, float* scale,
+                                void* stream) {
+  if (!stats || !scale || c4 % groups) return set_error(UR_ERR_ARG, "ur_adanaf_scales: bad arguments");
+  const size_t sh = (2 * static_cast<size_t>(c4) + groups) * sizeof(float);
+  adanaf_scales_kernel<<<batch, 256, sh, static_cast<cudaStream_t>(stream)>>>(stats, 1.0f / pixels, c4, groups, w_intra,
+                                                                             b_intra, w_inter, b_inter, scale);
+  UR_LAUNCH_CHECK("ur_adanaf_scales");
+}
+
+extern "C" int ur_tfa_gates(const double* stats, int pixels, int batch, int prompt_len, int dim, const float* cond,
+                            const float* w_out, const float* b_out, const float* w_pt, const float* b_pt, float* o,
+                            float* cond_next, void* stream) {
+  if (!stats || !cond || !w_out || !b_out || !o || (w_pt && (!b_pt || !cond_next)))
+    return set_error(UR_ERR_ARG, "ur_tfa_gates: bad arguments");
+  const size_t sh = (4 * static_cast<size_t>(prompt_len) * dim + 32) * sizeof(float);
+  if (sh > 48 * 1024) return set_error(UR_ERR_ARG, "ur_tfa_gates: prompt too large");
+  tfa_gates_kernel<<<batch, 256, sh, static_cast<cudaStream_t>(stream)>>>(stats, 1.0f / pixels, prompt_len, dim, cond,
+                                                                         w_out, b_out, w_pt, b_pt, o, cond_next);
+  UR_LAUNCH_CHECK("ur_tfa_gates");
+}
+
+extern "C" int ur_posterior_sample(const float* moments, const float* noise, float scaling_factor, int batch, int hw,
+                                   float* z, void* z_nhwc8, void* stream) {
+  if (!moments || !noise || !z) return set_error(UR_ERR_ARG, "ur_posterior_sample: bad arguments");
+  const long long total = static_cast<long long>(batch) * hw;
+  posterior_sample_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      moments, noise, scaling_factor, hw, total, z, static_cast<bf16*>(z_nhwc8));
+  UR_LAUNCH_CHECK("ur_posterior_sample");
+}
+
+extern "C" int ur_latent_axpby(const float* x, float a, const float* y, float b, int batch, int hw, float* out,
+                               void* out_nhwc8, float scale8, void* stream) {
+  if (!x || (!out && !out_nhwc8)) return set_error(UR_ERR_ARG, "ur_latent_axpby: bad arguments");
+  const long long total = static_cast<long long>(batch) * hw;
+  latent_axpby_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, a, y, b, hw, total, out, static_cast<bf16*>(out_nhwc8), scale8);
+  UR_LAUNCH_CHECK("ur_latent_axpby");
+}
+
+extern "C" int ur_ddim_step(float* x, const float* eps, int ld_eps, float sqrt_alpha_t, float sqrt_one_minus_alpha_t,
+                            float sqrt_alpha_prev, float sqrt_one_minus_alpha_prev, int clip_sample, int batch, int hw,
+                            void* x_nhwc8, void* stream) {
+  if (!x || !eps || ld_eps < 4) return set_error(UR_ERR_ARG, "ur_ddim_step: bad arguments");
+  const long long total = static_cast<long long>(batch) * hw;
+  ddim_step_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, eps, ld_eps, sqrt_alpha_t, sqrt_one_minus_alpha_t, sqrt_alpha_prev, sqrt_one_minus_alpha_prev, clip_sample, hw,
+      total, static_cast<bf16*>(x_nhwc8));
+  UR_LAUNCH_CHECK("ur_ddim_step");
+}
+
+extern "C" int ur_image_to_nhwc8(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch,
+                                 int channels, int h, int w, float a, float b, void* out, void* stream) {
+  if (!img || !out || channels > 8) return set_error(UR_ERR_ARG, "ur_image_to_nhwc8: bad arguments");
+  const long long total = static_cast<long long>(batch) * h * w;
+  image_to_nhwc8_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, sb, sc, sy, sx, channels, h,
+                                                                                       w, a, b, total,
+                                                                                       static_cast<bf16*>(out));
+  UR_LAUNCH_CHECK("ur_image_to_nhwc8");
+}
+
+extern "C" int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w,
+                                float a, float b, float* out, void* stream) {
+  if (!src || !out || h > hs || w > ws || channels > ld) return set_error(UR_ERR_ARG, "ur_nhwc_to_image: bad arguments");
+  const long long total = static_cast<long long>(batch) * channels * h * w;
+  nhwc_to_image_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld, hs, ws, channels, h, w, a,
+                                                                                      b, total, out);
+  UR_LAUNCH_CHECK("ur_nhwc_to_image");
+}

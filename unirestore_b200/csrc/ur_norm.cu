@@ -1,0 +1,288 @@
+// HBM-bound normalisation kernels on bf16 channels-last activations (128-bit vectorised):
+//   ur_chan_stats    per-(image, channel) sum / sum-of-squares in fp64   (GroupNorm / InstanceNorm / GAP)
+//   ur_norm_apply    GroupNorm / InstanceNorm apply (+affine, +SiLU), concatenating two sources
+//   ur_layernorm     per-token LayerNorm over C (nn.LayerNorm in BasicTransformerBlock, timm LayerNorm2d)
+//   ur_scale_channels  x[b, p, c] *= s[b, c]   (NAFBlock SCA nafnet_arch.py:122, AdaNAFV2 gates cfrm.py:49-52)
+#include "ur_common.cuh"
+#include "ur_host.h"
+
+namespace ur {
+
+// ------------------------------------------------------------------------------------ chan_stats
+// grid (chunks, B); block = CV * PL threads: thread (cv, pl) owns channel vector cv (8 channels)
+// and pixels p0+pl, p0+pl+PL, ...  fp32 per-thread partials -> shared fp32 atomics -> fp64 global atomics.
+__global__ void chan_stats_kernel(const bf16* __restrict__ x, long long ld, long long img_stride, int P, int C, int CV,
+                                  int PL, int chunk, double* __restrict__ stats, int stats_ld, int stats_off) {
+  extern __shared__ float sh[];  // [2][C]
+  const int b = blockIdx.y;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(P, p0 + chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const bf16* base = x + b * img_stride + cv * 8;
+  for (int p = p0 + pl; p < p1; p += PL) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + p * ld));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, c;
+      unpack_bf16(u[j], a, c);
+      s[2 * j] += a;
+      q[2 * j] += a * a;
+      s[2 * j + 1] += c;
+      q[2 * j + 1] += c * c;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[cv * 8 + j], s[j]);
+    atomicAdd(&sh[C + cv * 8 + j], q[j]);
+  }
+  __syncthreads();
+  double* out = stats + (static_cast<long long>(b) * stats_ld + stats_off) * 2;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(out + 2 * c, static_cast<double>(sh[c]));
+    atomicAdd(out + 2 * c + 1, static_cast<double>(sh[C + c]));
+  }
+}
+
+// ------------------------------------------------------------------------------------ norm_apply
+__global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, long long is1, int C1,
+                                  const bf16* __restrict__ x2, long long ld2, long long is2, int C2,
+                                  const double* __restrict__ stats, int G, int P, int CV, int PL, int chunk,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                  bf16* __restrict__ out, long long ldo, long long iso) {
+  extern __shared__ float sh[];  // mean[G], rstd[G]
+  const int C = C1 + C2;
+  const int cg = C / G;
+  const int b = blockIdx.y;
+  const double* st = stats + static_cast<long long>(b) * C * 2;
+  const double inv_n = 1.0 / (static_cast<double>(P) * cg);
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      s += st[2 * c];
+      q += st[2 * c + 1];
+    }
+    const double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sh[g] = static_cast<float>(mean);
+    sh[G + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int c0 = cv * 8;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const int g = c / cg;
+    const float ga = gamma ? __ldg(gamma + c) : 1.f;
+    const float be = beta ? __ldg(beta + c) : 0.f;
+    sc[j] = sh[G + g] * ga;
+    sf[j] = be - sh[g] * sc[j];
+  }
+  const bf16* src = (c0 < C1) ? (x1 + b * is1 + c0) : (x2 + b * is2 + (c0 - C1));
+  const long long lds = (c0 < C1) ? ld1 : ld2;
+  bf16* dst = out + b * iso + c0;
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(P, p0 + chunk);
+  for (int p = p0 + pl; p < p1; p += PL) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + p * lds));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, c;
+      unpack_bf16(u[j], a, c);
+      a = a * sc[2 * j] + sf[2 * j];
+      c = c * sc[2 * j + 1] + sf[2 * j + 1];
+      if (silu) {
+        a = silu_f(a);
+        c = silu_f(c);
+      }
+      o[j] = pack_bf16(a, c);
+    }
+    *reinterpret_cast<uint4*>(dst + p * ldo) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ layernorm
+// One warp per token; the row lives in registers (C <= 8*32*NV), exact two-pass mean / variance.
+template <int NV>
+__global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
+                                 int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int nvec = C >> 3;
+  float v[NV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vi * 8));
+      const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        unpack_bf16(u[j], v[i][2 * j], v[i][2 * j + 1]);
+        sum += v[i][2 * j] + v[i][2 * j + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+    if (vi < nvec) {
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = vi * 8 + 2 * j;
+        const float a = (v[i][2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        const float d = (v[i][2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+        o[j] = pack_bf16(a, d);
+      }
+      *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ scale_channels
+__global__ void scale_channels_kernel(bf16* __restrict__ x, long long ld, long long img_stride, int P, int CV,
+                                      const float* __restrict__ s, int s_ld) {
+  const int b = blockIdx.y;
+  const long long total = static_cast<long long>(P) * CV;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    const long long p = i / CV;
+    bf16* ptr = x + b * img_stride + p * ld + cv * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(ptr);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const float* sp = s + static_cast<long long>(b) * s_ld + cv * 8;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a, c;
+      unpack_bf16(u[j], a, c);
+      o[j] = pack_bf16(a * __ldg(sp + 2 * j), c * __ldg(sp + 2 * j + 1));
+    }
+    *reinterpret_cast<uint4*>(ptr) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static void pick_block(int C, int P, int& CV, int& PL, int& chunk, int& nchunks, int B) {
+  CV = C / 8;
+  PL = CV >= 256 ? 1 : 256 / CV;
+  if (PL < 1) PL = 1;
+  // aim for ~4 waves of blocks over the GPU, at least 8 pixels per thread
+  const int target = max(1, (4 * num_sms()) / max(1, B));
+  chunk = (P + target - 1) / target;
+  const int min_chunk = PL * 8;
+  if (chunk < min_chunk) chunk = min_chunk;
+  nchunks = (P + chunk - 1) / chunk;
+}
+
+}  // namespace ur
+
+using namespace ur;
+
+extern "C" int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int batch, int pixels, int channels,
+                             double* stats, int stats_ld, int stats_off, int zero_first, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x || !stats || channels % 8 || channels > 8192 || ld % 8 || img_stride % 8 || batch <= 0 || pixels <= 0)
+    return set_error(UR_ERR_ARG, "ur_chan_stats: bad arguments (C=%d ld=%lld)", channels, (long long)ld);
+  if (zero_first) {
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * static_cast<size_t>(batch) * stats_ld, stream);
+    if (e != cudaSuccess) return set_cuda_error(e, "ur_chan_stats memset");
+  }
+  int CV, PL, chunk, nchunks;
+  pick_block(channels, pixels, CV, PL, chunk, nchunks, batch);
+  dim3 grid(nchunks, batch);
+  chan_stats_kernel<<<grid, CV * PL, 2 * channels * sizeof(float), stream>>>(
+      static_cast<const bf16*>(x), ld, img_stride, pixels, channels, CV, PL, chunk, stats, stats_ld, stats_off);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_chan_stats launch");
+}
+
+extern "C" int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2,
+                             int64_t is2, int c2, const double* stats, int groups, int batch, int pixels,
+                             const float* gamma, const float* beta, float eps, int silu, void* out, int64_t ldo,
+                             int64_t iso, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int C = c1 + c2;
+  if (!x1 || !stats || !out || c1 % 8 || c2 % 8 || (c2 && !x2) || groups <= 0 || C % groups || C > 8192 || ld1 % 8 ||
+      ldo % 8 || (c2 && ld2 % 8))
+    return set_error(UR_ERR_ARG, "ur_norm_apply: bad arguments (C=%d+%d groups=%d)", c1, c2, groups);
+  int CV, PL, chunk, nchunks;
+  pick_block(C, pixels, CV, PL, chunk, nchunks, batch);
+  dim3 grid(nchunks, batch);
+  norm_apply_kernel<<<grid, CV * PL, 2 * groups * sizeof(float), stream>>>(
+      static_cast<const bf16*>(x1), ld1, is1, c1, static_cast<const bf16*>(x2), ld2, is2, c2, stats, groups, pixels, CV,
+      PL, chunk, gamma, beta, eps, silu, static_cast<bf16*>(out), ldo, iso);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_norm_apply launch");
+}
+
+extern "C" int ur_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int channels,
+                            const float* gamma, const float* beta, float eps, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x || !out || !gamma || !beta || channels % 8 || channels > 2048 || ldx % 8 || ldo % 8 || rows <= 0)
+    return set_error(UR_ERR_ARG, "ur_layernorm: bad arguments (C=%d)", channels);
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+  const bf16* xp = static_cast<const bf16*>(x);
+  bf16* op = static_cast<bf16*>(out);
+  const int M = static_cast<int>(rows);
+  if (channels <= 256)
+    layernorm_kernel<1><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+  else if (channels <= 512)
+    layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+  else if (channels <= 1280)
+    layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+  else
+    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_layernorm launch");
+}
+
+extern "C" int ur_scale_channels(void* x, int64_t ld, int64_t img_stride, int batch, int pixels, int channels,
+                                 const float* scale, int scale_ld, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!x || !scale || channels % 8 || ld % 8)
+    return set_error(UR_ERR_ARG, "ur_scale_channels: bad arguments");
+  const int CV = channels / 8;
+  const long long total = static_cast<long long>(pixels) * CV;
+  long long gxl = (total + 255) / 256;
+  if (gxl > 8LL * num_sms()) gxl = 8LL * num_sms();
+  int gx = static_cast<int>(gxl);
+  if (gx < 1) gx = 1;
+  scale_channels_kernel<<<dim3(gx, batch), 256, 0, stream>>>(static_cast<bf16*>(x), ld, img_stride, pixels, CV, scale,
+                                                           scale_ld);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_scale_channels launch");
+}

@@ -1,0 +1,121 @@
+"""``DiffUIE`` -- model assembly and the inference loop, reference unifie.py:22-169.
+
+    resize/pad -> ae.encode(+CFRM) -> noise at t=999 -> N x {Controller, ControlledUNet(+SC-Tuner), DDIM step}
+    -> ae.decode(+TFA) -> crop / resize
+
+The leftover FLOPs probe and unconditional ``raise`` at unifie.py:43-53 are not reproduced.  All per-step tensors
+stay on the GPU in bf16 channels-last; latents / noise / scheduler state are fp32; timesteps and the DDIM index
+math are host-side integers (bit-exact with the reference tables).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from .autoencoder import SkipConnectedAutoEncoder
+from .base_model import ControlledUNet
+from .controller import Controller, stablesr_config
+from .schedulers import DDIMScheduler, DDPMScheduler
+from .sd_blocks import AutoencoderKL, UNet2DConditionModel
+
+
+class DiffUIE(nn.Module):
+    def __init__(self, frenc=None, cnet=None, tedit=None, unet=None, vae=None, null_embeds=None):
+        super().__init__()
+        self.fr_type = frenc["type"] if frenc else None
+        self.control_type = cnet["type"] if cnet else None
+        self.tedit = tedit if tedit else None
+        self.ae = SkipConnectedAutoEncoder(vae or AutoencoderKL.from_pretrained("stabilityai/sd-turbo", subfolder="vae"),
+                                           self.fr_type, self.tedit)
+        if self.control_type:
+            self.controller = Controller(**stablesr_config)
+            self.base_model = ControlledUNet(
+                unet or UNet2DConditionModel.from_pretrained("stabilityai/sd-turbo", subfolder="unet"),
+                control_type=self.control_type, null_embeds=null_embeds)
+            self.register_buffer("train_timesteps", torch.tensor([249, 499, 749, 999, 999, 999], dtype=torch.int64))
+            self.ddpm = DDPMScheduler.from_pretrained("stabilityai/sd-turbo", subfolder="scheduler")
+            self.scheduler = DDIMScheduler.from_pretrained("stabilityai/sd-turbo", subfolder="scheduler")
+            self.scheduler.set_timesteps(cnet["num_inference_steps"], device=self.train_timesteps.device)
+        self._temb_cache = {}
+
+    # ---------------------------------------------------------------------------------- training-time helpers
+    def diffuse(self, latents, timesteps=None, noise=None):                      # unifie.py:77-89
+        if timesteps is None:
+            idx = torch.randint(0, len(self.train_timesteps), (latents.size(0),), device=latents.device)
+            timesteps = self.train_timesteps.to(latents.device)[idx]
+        if noise is None:
+            noise = torch.randn_like(latents)
+        ts = [int(t) for t in timesteps.reshape(-1).tolist()]
+        if len(set(ts)) == 1:
+            sa, sb = self.ddpm.noise_coefficients(ts[0])
+            out, _ = ops.latent_axpby(latents.float().contiguous(), sa, noise.float().contiguous(), sb)
+        else:                                                                       # per-sample timesteps
+            out = torch.empty_like(latents, dtype=torch.float32)
+            for i, t in enumerate(ts):
+                sa, sb = self.ddpm.noise_coefficients(t)
+                out[i:i + 1], _ = ops.latent_axpby(latents[i:i + 1].float().contiguous(), sa,
+                                                   noise[i:i + 1].float().contiguous(), sb)
+        return out, noise, timesteps
+
+    def _embeddings(self, t: int, device):
+        """Controller / UNet timestep embeddings of integer timestep t (cached: they only depend on weights)."""
+        key = (int(t), str(device))
+        if key not in self._temb_cache:
+            ts = torch.tensor([int(t)], dtype=torch.int64, device=device)
+            self._temb_cache[key] = (self.controller.time_embed(ts), self.base_model.time_embed(ts))
+        return self._temb_cache[key]
+
+    def clear_caches(self):
+        self._temb_cache = {}
+        for m in self.modules():
+            if hasattr(m, "invalidate"):
+                m.invalidate()
+
+    def predict_eps(self, zt8, z0_8, t: int):
+        emb_c, emb_u = self._embeddings(t, zt8.device)
+        control = self.controller.run(z0_8, emb_c)                               # unifie.py:148
+        return self.base_model.run(zt8, control, emb_u)                          # unifie.py:149
+
+    def predict_z0(self, latents, conditions, timesteps):                        # unifie.py:91-105
+        ts = sorted(set(int(t) for t in timesteps.reshape(-1).tolist()))
+        if len(ts) != 1:
+            raise NotImplementedError("predict_z0: one timestep per call on the CUDA path")
+        eps8 = self.predict_eps(ops.image_to_nhwc8(latents.float()), ops.image_to_nhwc8(conditions.float()), ts[0])
+        sa, sb = self.ddpm.noise_coefficients(ts[0])
+        z = latents.float().clone()
+        # x0 = (x - sqrt(1-a) eps) / sqrt(a): the DDIM kernel with a_prev = 1 (sqrt(a_p) = 1, sqrt(1-a_p) = 0)
+        ops.ddim_step_(z, eps8, (sa, sb, 1.0, 0.0), want_nhwc8=False)
+        return z
+
+    # ---------------------------------------------------------------------------------- inference (hot path)
+    def restore_latents(self, z0, z0_8, noise=None):
+        """The N-step loop of unifie.py:141-150 on fp32 NCHW latents; returns the denoised latents."""
+        if noise is None:
+            noise = torch.randn_like(z0)
+        sa, sb = self.ddpm.noise_coefficients(999)                               # unifie.py:141-144
+        zt, zt8 = ops.latent_axpby(z0, sa, noise.float().contiguous(), sb, want_nhwc8=True)
+        for t in self.scheduler.timesteps_host:                                  # unifie.py:146-150
+            eps8 = self.predict_eps(zt8, z0_8, t)
+            zt8 = ops.ddim_step_(zt, eps8, self.scheduler.step_coefficients(t), bool(self.scheduler.config.clip_sample))
+        return zt
+
+    @torch.no_grad()
+    def forward(self, images, task, noise=None):
+        """images fp32 [B,3,H,W] in [0,1] -> restored fp32 [B,3,H,W].  ``noise=(posterior, diffuse)`` injects the two
+        RNG draws of the reference (autoencoder.py:152, unifie.py:87) for parity runs."""
+        org_h, org_w = images.shape[-2:]
+        h, w = org_h, org_w
+        images = images.float()
+        if h < 512 or w < 512:                                                   # unifie.py:124-129
+            s = 512 / min(h, w)
+            h, w = round(h * s), round(w * s)
+            images = F.interpolate(images, (h, w), mode="bicubic", align_corners=False, antialias=False)
+        if h % 64 or w % 64:                                                     # unifie.py:130-134
+            images = F.pad(images, (0, (64 - w % 64) % 64, 0, (64 - h % 64) % 64), mode="reflect")
+        n_post, n_diff = noise if noise is not None else (None, None)
+        z0, z0_8, mids = self.ae.run_encode(images, enable_fr=self.fr_type is not None, noise=n_post)
+        zt = self.restore_latents(z0, z0_8, n_diff) if self.control_type else z0
+        preds = self.ae.run_decode(zt, mids, task, crop_hw=(h, w))               # unifie.py:155,164
+        if (h, w) != (org_h, org_w):                                             # unifie.py:165-168
+            preds = F.interpolate(preds, (org_h, org_w), mode="bicubic", align_corners=False, antialias=False)
+        return preds

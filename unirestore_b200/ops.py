@@ -68,7 +68,11 @@ def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None
         x2 = _as4(x2)
         if x2.shape[:3] != x.shape[:3]:
             raise ValueError("x2 spatial shape mismatch")
-        C2, ld2 = x2.shape[3], _check_nhwc(x2, "x2")
+        if C1 % 64:      # the two-source TMA path needs 64-aligned source-1 channels: materialise the concat
+            x, x2 = torch.cat([x, x2], dim=-1), None
+            C1, ld1 = x.shape[3], x.shape[3]
+        else:
+            C2, ld2 = x2.shape[3], _check_nhwc(x2, "x2")
     hout = H // stride if hout is None else hout
     wout = W // stride if wout is None else wout
     gated = act in (UR_ACT_GEGLU, UR_ACT_GATE)
@@ -81,13 +85,17 @@ def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None
         out = _as4(out)
         if tuple(out.shape) != (B, hout, wout, n_out) or (out.stride(3) != 1 and n_out != 1):
             raise ValueError("out shape %s != %s" % (tuple(out.shape), (B, hout, wout, n_out)))
-    if w.dtype != torch.bfloat16 or not w.is_contiguous():
-        raise ValueError("w must be contiguous bf16")
+    if w.dtype != torch.bfloat16 or w.stride(-1) != 1:
+        raise ValueError("w must be bf16 with unit K stride")
+    if (w.dim() == 3) != bool(w_batched):
+        raise ValueError("w must be [n, k] (shared) or [batch, n, k] (w_batched)")
     d = ConvDesc()
     d.x1, d.x2 = x.data_ptr(), (x2.data_ptr() if x2 is not None else None)
     d.c1, d.c2, d.ld1, d.ld2 = C1, C2, ld1, ld2
     d.batch, d.hin, d.win = B, H, W
     d.w, d.w_batched, d.n = w.data_ptr(), int(w_batched), n
+    d.w_ld = w.stride(-2)
+    d.w_bs = w.stride(0) if w_batched else 0
     d.ntaps = len(taps)
     for i, (dy, dx) in enumerate(taps):
         d.tap_dy[i], d.tap_dx[i] = dy, dx
@@ -141,3 +149,230 @@ def pack_gated_weight(w2d: torch.Tensor, bias: torch.Tensor | None, bn: int):
     wp = w2d[src].contiguous()
     bp = bias[src].contiguous() if bias is not None else None
     return wp, bp
+
+
+# ----------------------------------------------------------------------------------------------- helpers
+def _lib():
+    return _cabi.lib()
+
+
+def _geom(x):
+    """(batch, pixels, channels, ld, img_stride) of an NHWC / [B,T,C] bf16 activation (channel-slice views ok)."""
+    x4 = _as4(x)
+    ld = _check_nhwc(x4, "x")
+    B, H, W, Cc = x4.shape
+    return B, H * W, Cc, ld, (x4.stride(0) if B > 1 else H * W * ld)
+
+
+def _f32(t, name):
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda):
+        raise ValueError("%s must be a contiguous CUDA fp32 tensor" % name)
+    return _ptr(t)
+
+
+# ----------------------------------------------------------------------------------------------- normalisation
+def chan_stats(x, stats=None, offset=0, total_channels=None, zero=True):
+    """fp64 (sum, sumsq) per (image, channel) -> ``[B, total_channels, 2]``."""
+    B, P, Cc, ld, ist = _geom(x)
+    total = total_channels or Cc
+    if stats is None:
+        stats = torch.empty((B, total, 2), device=x.device, dtype=torch.float64)
+    check(_lib().ur_chan_stats(_ptr(x), ld, ist, B, P, Cc, _ptr(stats), total, offset, int(zero), _stream()),
+          "ur_chan_stats")
+    return stats
+
+
+def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None):
+    """GroupNorm / InstanceNorm apply on ``cat(x, x2)`` (channel dim); returns a dense bf16 tensor."""
+    B, P, C1, ld1, is1 = _geom(x)
+    C2, ld2, is2 = 0, 0, 0
+    if x2 is not None:
+        B2, P2, C2, ld2, is2 = _geom(x2)
+        if (B2, P2) != (B, P):
+            raise ValueError("x2 shape mismatch")
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (C1 + C2,), device=x.device, dtype=torch.bfloat16)
+    _, _, Co, ldo, iso = _geom(out)
+    check(_lib().ur_norm_apply(_ptr(x), ld1, is1, C1, _ptr(x2), ld2, is2, C2, _ptr(stats), groups, B, P,
+                               _f32(gamma, "gamma"), _f32(beta, "beta"), eps, int(silu), _ptr(out), ldo, iso,
+                               _stream()), "ur_norm_apply")
+    return out
+
+
+def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
+    """nn.GroupNorm (+SiLU) over ``cat(x, x2)``: two launches (statistics, apply)."""
+    C1 = x.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    stats = chan_stats(x, total_channels=C1 + C2)
+    if x2 is not None:
+        chan_stats(x2, stats=stats, offset=C1, total_channels=C1 + C2, zero=False)
+    return norm_apply(x, stats, groups, gamma, beta, eps, silu, x2)
+
+
+def layernorm(x, gamma, beta, eps):
+    B, P, Cc, ld, ist = _geom(x)
+    if B > 1 and ist != P * ld:
+        raise ValueError("layernorm needs a dense token matrix")
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib().ur_layernorm(_ptr(x), ld, _ptr(out), Cc, B * P, Cc, _f32(gamma, "gamma"), _f32(beta, "beta"), eps,
+                              _stream()), "ur_layernorm")
+    return out
+
+
+def scale_channels_(x, scale):
+    B, P, Cc, ld, ist = _geom(x)
+    check(_lib().ur_scale_channels(_ptr(x), ld, ist, B, P, Cc, _f32(scale, "scale"), scale.shape[-1], _stream()),
+          "ur_scale_channels")
+    return x
+
+
+# ----------------------------------------------------------------------------------------------- attention (unfused)
+def softmax_rows(scores, n_valid, n_pad):
+    rows = scores.numel() // scores.shape[-1]
+    probs = torch.empty(tuple(scores.shape[:-1]) + (n_pad,), device=scores.device, dtype=torch.bfloat16)
+    check(_lib().ur_softmax_rows(_ptr(scores), scores.stride(-2), _ptr(probs), n_pad, rows, n_valid, n_pad, _stream()),
+          "ur_softmax_rows")
+    return probs
+
+
+def transpose_tokens(x, tokens_pad=None):
+    """bf16 [B, T, d] (channel-slice view ok) -> dense [B, d, Tpad] with zero padding."""
+    B, T, d = x.shape
+    tokens_pad = tokens_pad or ((T + 7) // 8) * 8
+    out = torch.empty((B, d, tokens_pad), device=x.device, dtype=torch.bfloat16)
+    check(_lib().ur_transpose_tokens(_ptr(x), x.stride(1), x.stride(0), B, T, d, _ptr(out), tokens_pad, _stream()),
+          "ur_transpose_tokens")
+    return out
+
+
+def attention(q, k, v, heads, out=None):
+    """softmax(q k^T / sqrt(d)) v per head.  q [B,Tq,C], k/v [B or 1,Tk,C] bf16 (channel-slice views ok).
+
+    Unfused v1 path: per head S = QK^T (ur_conv_gemm, fp32) -> ur_softmax_rows -> O = P V^T (ur_conv_gemm)."""
+    B, Tq, Cc = q.shape
+    Tk = k.shape[1]
+    d = Cc // heads
+    shared = k.shape[0] == 1 and B > 1          # one K/V for every image (constant prompt, base_model.py:221)
+    if out is None:
+        out = torch.empty((B, Tq, Cc), device=q.device, dtype=torch.bfloat16)
+    tk_pad = ((Tk + 7) // 8) * 8
+    scale = float(d) ** -0.5
+    for h in range(heads):
+        sl = slice(h * d, (h + 1) * d)
+        kh = k[0, :, sl] if shared else k[..., sl]
+        s = conv_gemm(q[..., sl], kh, Tk, w_batched=not shared, alpha=scale, out_dtype=torch.float32)
+        p = softmax_rows(s, Tk, tk_pad)
+        vt = transpose_tokens(v[..., sl], tk_pad)
+        conv_gemm(p, vt[0] if shared else vt, d, w_batched=not shared, out=out[..., sl])
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- CFRM / TFA helpers
+def dwconv3x3_gate(x, weight9, bias):
+    """x bf16 [B,H,W,2c] dense -> (y bf16 [B,H,W,c], stats fp64 [B,c,2] with the per-channel sums of y)."""
+    B, H, W, C2 = x.shape
+    if not x.is_contiguous():
+        raise ValueError("dwconv3x3_gate needs a dense input")
+    c = C2 // 2
+    y = torch.empty((B, H, W, c), device=x.device, dtype=torch.bfloat16)
+    stats = torch.empty((B, c, 2), device=x.device, dtype=torch.float64)
+    check(_lib().ur_dwconv3x3_gate(_ptr(x), B, H, W, c, _f32(weight9, "weight"), _f32(bias, "bias"), _ptr(y),
+                                   _ptr(stats), _stream()), "ur_dwconv3x3_gate")
+    return y, stats
+
+
+ACT_IDS = {None: 0, "silu": 1, "gelu": 2, "tanh": 3}
+
+
+def small_linear(x, w, bias=None, groups=1, act_in=None, act_out=None, stats_scale=None):
+    """Tiny fp32 linear ``[B,K] -> [B,N]``; ``stats_scale`` set: x is a chan_stats array, input = sum * stats_scale."""
+    n, k = w.shape
+    if stats_scale is not None:
+        B, x_ld, mode, sc = x.shape[0], x.shape[1], 1, float(stats_scale)
+    else:
+        _f32(x, "x")
+        B, x_ld, mode, sc = x.shape[0], x.shape[1], 0, 1.0
+    y = torch.empty((B, n), device=w.device, dtype=torch.float32)
+    check(_lib().ur_small_linear(_ptr(x), mode, sc, x_ld, _f32(w, "w"), _f32(bias, "bias"), _ptr(y), n, B, n, k,
+                                 groups, ACT_IDS[act_in], ACT_IDS[act_out], _stream()), "ur_small_linear")
+    return y
+
+
+def timestep_embedding(timesteps, dim):
+    if timesteps.dtype != torch.int64 or not timesteps.is_cuda:
+        raise ValueError("timesteps must be a CUDA int64 tensor")
+    B = timesteps.numel()
+    out = torch.empty((B, dim), device=timesteps.device, dtype=torch.float32)
+    check(_lib().ur_timestep_embedding(_ptr(timesteps.contiguous()), B, dim, _ptr(out), _stream()),
+          "ur_timestep_embedding")
+    return out
+
+
+def adanaf_scales(stats, pixels, groups, w_intra, b_intra, w_inter, b_inter):
+    B, C4 = stats.shape[0], stats.shape[1]
+    scale = torch.empty((B, C4), device=stats.device, dtype=torch.float32)
+    check(_lib().ur_adanaf_scales(_ptr(stats), pixels, B, C4, groups, _f32(w_intra, "w_intra"),
+                                  _f32(b_intra, "b_intra"), _f32(w_inter, "w_inter"), _f32(b_inter, "b_inter"),
+                                  _ptr(scale), _stream()), "ur_adanaf_scales")
+    return scale
+
+
+def tfa_gates(stats, pixels, cond, w_out, b_out, w_pt=None, b_pt=None):
+    B, T, D = cond.shape
+    o = torch.empty((B, D), device=cond.device, dtype=torch.float32)
+    nxt = torch.empty((B, T, D // 2), device=cond.device, dtype=torch.float32) if w_pt is not None else None
+    check(_lib().ur_tfa_gates(_ptr(stats), pixels, B, T, D, _f32(cond, "cond"), _f32(w_out, "w_out"),
+                              _f32(b_out, "b_out"), _f32(w_pt, "w_pt"), _f32(b_pt, "b_pt"), _ptr(o), _ptr(nxt),
+                              _stream()), "ur_tfa_gates")
+    return o, nxt
+
+
+# ----------------------------------------------------------------------------------------------- latents / images
+def posterior_sample(moments, noise, scaling_factor):
+    """moments fp32 [B,h,w,8] channels-last, noise fp32 [B,4,h,w] -> (z fp32 [B,4,h,w], z8 bf16 [B,h,w,8])."""
+    B, h, w, _ = moments.shape
+    z = torch.empty((B, 4, h, w), device=moments.device, dtype=torch.float32)
+    z8 = torch.empty((B, h, w, 8), device=moments.device, dtype=torch.bfloat16)
+    check(_lib().ur_posterior_sample(_f32(moments, "moments"), _f32(noise, "noise"), scaling_factor, B, h * w, _ptr(z),
+                                     _ptr(z8), _stream()), "ur_posterior_sample")
+    return z, z8
+
+
+def latent_axpby(x, a, y=None, b=0.0, want_out=True, want_nhwc8=False, scale8=1.0):
+    B, _, h, w = x.shape
+    out = torch.empty_like(x) if want_out else None
+    out8 = torch.empty((B, h, w, 8), device=x.device, dtype=torch.bfloat16) if want_nhwc8 else None
+    check(_lib().ur_latent_axpby(_f32(x, "x"), a, _f32(y, "y"), b, B, h * w, _ptr(out), _ptr(out8), scale8, _stream()),
+          "ur_latent_axpby")
+    return out, out8
+
+
+def ddim_step_(x, eps_nhwc, coefs, clip_sample=False, want_nhwc8=True):
+    """In-place DDIM update of fp32 NCHW latents ``x``; ``eps_nhwc`` fp32 [B,h,w,ld>=4]."""
+    B, _, h, w = x.shape
+    x8 = torch.empty((B, h, w, 8), device=x.device, dtype=torch.bfloat16) if want_nhwc8 else None
+    sa, sb, sap, sbp = coefs
+    check(_lib().ur_ddim_step(_f32(x, "x"), _f32(eps_nhwc, "eps"), eps_nhwc.shape[-1], sa, sb, sap, sbp,
+                              int(clip_sample), B, h * w, _ptr(x8), _stream()), "ur_ddim_step")
+    return x8
+
+
+def image_to_nhwc8(img, a=1.0, b=0.0):
+    """fp32 [B,C<=8,H,W] (any strides) -> bf16 [B,H,W,8] = a*img+b, zero channel padding."""
+    if img.dtype != torch.float32 or not img.is_cuda:
+        raise ValueError("img must be a CUDA fp32 tensor")
+    B, Cc, H, W = img.shape
+    out = torch.empty((B, H, W, 8), device=img.device, dtype=torch.bfloat16)
+    check(_lib().ur_image_to_nhwc8(_ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), B, Cc, H, W,
+                                   a, b, _ptr(out), _stream()), "ur_image_to_nhwc8")
+    return out
+
+
+def nhwc_to_image(src, channels, h=None, w=None, a=1.0, b=0.0):
+    """fp32 channels-last [B,Hs,Ws,ld] -> fp32 NCHW [B,channels,h,w] = a*src+b (top-left crop)."""
+    B, Hs, Ws, ld = src.shape
+    h, w = h or Hs, w or Ws
+    out = torch.empty((B, channels, h, w), device=src.device, dtype=torch.float32)
+    check(_lib().ur_nhwc_to_image(_f32(src, "src"), ld, Hs, Ws, B, channels, h, w, a, b, _ptr(out), _stream()),
+          "ur_nhwc_to_image")
+    return out
