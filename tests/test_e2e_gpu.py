@@ -1,0 +1,77 @@
+"""End-to-end parity of the CUDA path against the golden fixtures produced by executing the reference's own
+files (oracle/make_golden.py): ControlledUNet (a6), encode/decode (a2/a9, with CFRM + TFA) and DiffUIE.forward (a1)
+on deterministic name-keyed weights.  bf16 pipeline vs fp32 reference -> rel-L2 gates written per test."""
+import os
+
+import pytest
+import torch
+
+from tests.util import assert_close
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+CFG = (dict(type="CFRM"), dict(type="scedit", num_inference_steps=2), dict(type="TFA", prompt_len=1, task=["ir", "cls", "seg"]))
+
+
+def rnd(seed, *shape, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+@pytest.fixture(scope="module")
+def model():
+    from unirestore_b200.diffuie import DiffUIE
+    from unirestore_b200.init_utils import deterministic_init_
+    m = DiffUIE(*CFG).eval().requires_grad_(False)
+    deterministic_init_(m)
+    return m.to(DEV)
+
+
+def test_state_dict_contract(model):
+    """Attribute paths / key prefixes the reference's checkpoint surgery relies on (engine_unifie.py:49-133)."""
+    keys = list(model.state_dict())
+    for prefix in ("ae.vae.encoder.fr_blocks.", "controller.", "base_model.csc_editors.", "ae.vae.decoder.task_prompts.",
+                   "ae.vae.decoder.task_editors.", "base_model.unet.", "ae.vae.encoder.", "ae.vae.decoder."):
+        assert any(k.startswith(prefix) for k in keys), prefix
+    assert model.base_model.null_embeds.shape == (1, 77, 1024)
+    assert model.scheduler.timesteps.tolist() == [999, 499]
+
+
+def test_controlled_unet_golden(model):
+    g = torch.load(os.path.join(GOLD, "base_model.pt"))
+    c = torch.load(os.path.join(GOLD, "controller.pt"))
+    control = {k: v.to(DEV) for k, v in c["out"].items()}
+    zt = rnd(g["zt_seed"], *g["zt_shape"]).to(DEV)
+    y = model.base_model(zt, control, torch.tensor([g["t"]], device=DEV))
+    assert_close(y, g["out"].to(DEV), 3e-2, "ControlledUNet vs reference golden")
+
+
+def test_autoencoder_golden(model):
+    g = torch.load(os.path.join(GOLD, "autoencoder.pt"))
+    gen = torch.Generator().manual_seed(g["img_seed"])
+    img = torch.rand(*g["img_shape"], generator=gen).to(DEV)
+    torch.manual_seed(g["rng_seed"])
+    noise = torch.randn(1, 4, g["img_shape"][2] // 8, g["img_shape"][3] // 8).to(DEV)
+    z, skips = model.ae.encode(img, enable_fr=True, noise=noise)
+    assert_close(z, g["z"].to(DEV), 3e-2, "encode z vs reference golden")
+    for i, s in enumerate(skips):
+        assert_close(s.float()[..., ::4, ::4], g["skips"][i]["sample"].to(DEV), 3e-2, "encode skip%d" % i)
+    # decode from the REFERENCE latents/skips is not possible (goldens keep sub-sampled skips): decode our own
+    for task in ("ir", "seg"):
+        y = model.ae.decode(z, skips, task)
+        assert_close(y, g["decode"][task].to(DEV), 5e-2, "decode[%s] vs reference golden" % task)
+    with pytest.raises(KeyError):
+        model.ae.decode(z, skips, "no-such-task")
+
+
+def test_diffuie_forward_golden(model):
+    g = torch.load(os.path.join(GOLD, "diffuie.pt"))
+    gen = torch.Generator().manual_seed(g["img_seed"])
+    img = torch.rand(*g["img_shape"], generator=gen).to(DEV)
+    torch.manual_seed(g["rng_seed"])
+    n_post, n_diff = torch.randn(1, 4, 64, 80), torch.randn(1, 4, 64, 80)
+    assert model.scheduler.timesteps.tolist() == g["timesteps"].tolist()
+    y = model(img, g["task"], noise=(n_post.to(DEV), n_diff.to(DEV)))
+    assert y.shape == g["out"].shape
+    assert_close(y, g["out"].to(DEV), 1e-1, "DiffUIE.forward (2 DDIM steps, 512x640) vs reference golden")

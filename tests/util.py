@@ -19,7 +19,19 @@ def assert_close(got, ref, tol, what=""):
         bad = (d > 0.05 * ref.abs().max()).float().mean().item()
         raise AssertionError("%s: rel-L2 %.3e > %.1e; max|d| %.4g at %s (got %.5g ref %.5g); %.2f%% elems off by >5%% of max"
                              % (what, e, tol, d.max().item(), idx, got[tuple(idx)].item(), ref[tuple(idx)].item(), 100 * bad))
+    _log("%-60s rel-L2 %.3e (tol %.0e)" % (what, e, tol))
     return e
+
+
+def _log(line):
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity.log"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
 
 
 def bf16_round(t):

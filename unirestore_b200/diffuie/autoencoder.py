@@ -80,7 +80,11 @@ class SkipConnectedAutoEncoder(nn.Module):
     def run_decode(self, latents, skips, task, crop_hw=None):
         """latents fp32 [B,4,h,w], skips bf16 NHWC, task key -> fp32 [B,3,H,W] = (decoder + 1) / 2."""
         dec, pk, vp = self.vae.decoder, self.vae.decoder.pk, self.vae.pk
-        prompt = dec.task_prompts[task] if self.tedit_type else None          # KeyError for an unknown task (ref :47)
+        prompt = None
+        if self.tedit_type:
+            if task not in dec.task_prompts:                                 # `task_prompts[task]` (autoencoder.py:47)
+                raise KeyError(task)
+            prompt = dec.task_prompts[task]
         _, z8 = ops.latent_axpby(latents.float().contiguous(), 1.0, want_out=False, want_nhwc8=True,
                                  scale8=1.0 / float(self.vae.config["scaling_factor"]))          # autoencoder.py:170
         z8 = ops.conv_gemm(z8, vp["wpq"], 8, bias=vp["bpq"])
