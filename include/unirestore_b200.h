@@ -118,6 +118,12 @@ int ur_scale_channels(void* x, int64_t ld, int64_t img_stride, int batch, int pi
  * Attention helpers (unfused path: S = QK^T by ur_conv_gemm, softmax here, O = P V by ur_conv_gemm)
  * diffusers Attention / F.scaled_dot_product_attention (controller.py:183-185, VAE mid block, base_model.py:138).
  * ---------------------------------------------------------------------------------------------- */
+/* Fused flash-style attention on tcgen05/TMEM (head_dim 64 or 128): out[b,q,h*d:(h+1)*d] = softmax(q k^T * scale) v.
+ * q/k/v/out are bf16 token matrices addressed as ptr + b*bs + token*ld + h*head_dim (channel-slice views of a packed
+ * qkv buffer are fine); kv_shared = 1: k/v have no batch dimension (the constant null prompt, base_model.py:221). */
+int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void* k, int64_t ldk, int64_t k_bs, const void* v,
+                 int64_t ldv, int64_t v_bs, void* out, int64_t ldo, int64_t out_bs, int batch, int heads, int head_dim,
+                 int tq, int tk, int kv_shared, float scale, void* stream);
 int ur_softmax_rows(const float* scores, int64_t ld_s, void* probs, int64_t ld_p, int64_t rows, int n_valid, int n_pad,
                     void* stream);
 int ur_transpose_tokens(const void* x, int64_t ld, int64_t batch_stride, int batch, int tokens, int dim, void* out,

@@ -1,0 +1,61 @@
+"""ur_attention (fused tcgen05 flash attention) and the unfused GEMM/softmax/GEMM path against fp32
+F.scaled_dot_product_attention on the same bf16-rounded q/k/v.  Gate: rel-L2 <= 3e-3 after rounding the reference to
+bf16 (P is rounded to bf16 before the second GEMM, as every flash kernel does)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import assert_close, bf16_round
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(torch.bfloat16)
+
+
+def _ref(q, k, v, heads):
+    B, Tq, C = q.shape
+    d = C // heads
+    sp = lambda t: t.float().view(t.shape[0], -1, heads, d).transpose(1, 2)
+    o = F.scaled_dot_product_attention(sp(q), sp(k).expand(B, -1, -1, -1), sp(v).expand(B, -1, -1, -1))
+    return bf16_round(o.transpose(1, 2).reshape(B, Tq, C))
+
+
+@pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 5, 64, 256, 256), (1, 2, 64, 128, 128), (2, 4, 64, 200, 300),
+                                             (1, 5, 64, 4096, 4096), (2, 4, 128, 64, 64), (3, 4, 128, 256, 256),
+                                             (2, 20, 64, 4, 4), (1, 10, 64, 1024, 1024), (2, 1, 64, 130, 7)])
+def test_fused_self_attention_packed_qkv(B, heads, d, Tq, Tk):
+    from unirestore_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    C = heads * d
+    if Tq == Tk:     # packed [B,T,3C] buffer, channel-slice views (the layout the QKV GEMM writes)
+        qkv = _rand(B, Tq, 3 * C, seed=1, scale=1.5)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q, k, v = _rand(B, Tq, C, seed=2, scale=1.5), _rand(B, Tk, C, seed=3, scale=1.5), _rand(B, Tk, C, seed=4)
+    y = ops.attention(q, k, v, heads)
+    assert_close(y, _ref(q, k, v, heads), 3e-3, "flash attention %s" % ((B, heads, d, Tq, Tk),))
+
+
+@pytest.mark.parametrize("B,heads,Tq", [(4, 5, 4096), (2, 10, 1024), (3, 20, 64)])
+def test_fused_cross_attention_shared_kv(B, heads, Tq):
+    """K/V of the constant 77-token null prompt shared by all images (base_model.py:221)."""
+    from unirestore_b200 import ops
+    C = heads * 64
+    q = _rand(B, Tq, C, seed=5, scale=1.5)
+    kv = _rand(1, 77, 2 * C, seed=6, scale=1.5)
+    k, v = kv[..., :C], kv[..., C:]
+    y = ops.attention(q, k, v, heads)
+    assert_close(y, _ref(q, k, v, heads), 3e-3, "flash cross attention %s" % ((B, heads, Tq),))
+
+
+@pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 1, 512, 96, 96), (1, 1, 512, 1024, 1024), (2, 5, 64, 64, 77)])
+def test_unfused_attention(B, heads, d, Tq, Tk):
+    from unirestore_b200 import ops
+    C = heads * d
+    q, k, v = _rand(B, Tq, C, seed=7), _rand(B, Tk, C, seed=8), _rand(B, Tk, C, seed=9)
+    y = ops.attention_unfused(q, k, v, heads)
+    assert_close(y, _ref(q, k, v, heads), 3e-3, "unfused attention %s" % ((B, heads, d, Tq, Tk),))

@@ -54,6 +54,8 @@ SIGNATURES = {
                                 _I64, _P]),
     "ur_layernorm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P]),
     "ur_scale_channels": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _P]),
+    "ur_attention": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _P, _I64, _I64, _I, _I, _I, _I, _I, _I, _F,
+                               _P]),
     "ur_softmax_rows": (C.c_int, [_P, _I64, _P, _I64, _I64, _I, _I, _P]),
     "ur_transpose_tokens": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _P]),
     "ur_dwconv3x3_gate": (C.c_int, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
@@ -85,7 +87,12 @@ def lib():
     return _lib
 
 
+launch_count = 0          # C-ABI compute calls issued (each is >= 1 kernel launch); read by bench.py
+
+
 def check(rc: int, what: str = ""):
+    global launch_count
+    launch_count += 1
     if rc != 0:
         raise UrError("%s failed (%d): %s" % (what or "unirestore_b200 call", rc,
                                               lib().ur_last_error().decode(errors="replace")))

@@ -1,0 +1,326 @@
+// ur_attention: fused scaled-dot-product attention (flash-style, online softmax) on tcgen05 / TMEM.
+//
+//   O[b, q, h*D:(h+1)*D] = softmax(Q K^T / sqrt(D)) V      per (image b, head h), D in {64, 128}
+//
+// One CTA per (128-query tile, head, image); KV is streamed in tiles of 128 keys:
+//   warp 0      TMA producer: Q once, then a 2-stage ring of (K_j, V_j) tiles (128-byte swizzled boxes)
+//   warp 1      single-thread tcgen05.mma issuer:  S = Q K_j^T   (128x128 fp32 in TMEM columns [0,128))
+//                                                   T = P_j V_j   (128xD   fp32 in TMEM columns [128,128+D))
+//   warps 2..5  softmax: ONE THREAD PER QUERY ROW (TMEM lane) -> row max / sum need no shuffles.  Two TMEM passes
+//               over S (max, then exp2 + bf16 pack), P_j written to shared memory in the K-major SW128 UMMA
+//               layout, running O kept in registers and rescaled by exp2(m_old - m_new) per tile.
+// P V^T uses V exactly as TMA lands it ([keys, D] rows of 128 B) through an MN-major UMMA descriptor.
+// With D = 64 a CTA needs 112 KB smem and 256 TMEM columns, so two CTAs share an SM and one CTA's softmax
+// overlaps the other's MMAs.
+//
+// Reference arithmetic: F.scaled_dot_product_attention inside diffusers Attention (BasicTransformerBlock
+// attn1/attn2 at base_model.py:138,159,191; Controller AttnDownBlock2D / mid block controller.py:101-141).
+#include "ur_common.cuh"
+#include "ur_host.h"
+
+namespace ur {
+
+struct AttnParams {
+  int Tq, Tk, heads;
+  int kv_shared;          // K/V have no batch dimension (constant prompt)
+  float scale_log2;       // softmax scale * log2(e)
+  bf16* out;
+  long long ldo, out_bs;
+};
+
+constexpr int kTileQ = 128;
+constexpr int kTileK = 128;
+
+template <int D>
+__global__ void __launch_bounds__(192, D == 64 ? 2 : 1)
+attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
+                 const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
+  constexpr int ND = D / 64;                       // 64-column blocks per head
+  constexpr int kQBytes = kTileQ * D * 2;
+  constexpr int kKBytes = kTileK * D * 2;
+  constexpr int kPBytes = kTileQ * kTileK * 2;      // 32 KB: two K-major blocks of [128 x 64]
+  constexpr int kStages = 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kQBytes;                      // stage s: K at s*2*kKBytes, V right after
+  uint8_t* sP = sKV + kStages * 2 * kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;                     // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;           // [kStages]
+  uint64_t* s_full = kv_empty + kStages;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* o_full = p_full + 1;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTileQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = (p.Tk + kTileK - 1) / kTileK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_T = tmem_base + 128;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+#pragma unroll
+      for (int nb = 0; nb < ND; ++nb) tma_load_3d(sQ + nb * (kTileQ * 128), &mapQ, q_full, h * D + nb * 64, q0, b);
+      const int bk = p.kv_shared ? 0 : b;
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * kKBytes);
+        uint8_t* sk = sKV + s * 2 * kKBytes;
+#pragma unroll
+        for (int nb = 0; nb < ND; ++nb) {
+          tma_load_3d(sk + nb * (kTileK * 128), &mapK, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
+          tma_load_3d(sk + kKBytes + nb * (kTileK * 128), &mapV, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
+      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
+        const uint32_t aK = smem_u32(sKV + s * 2 * kKBytes);
+        const uint32_t aV = aK + kKBytes;
+        // ---- S = Q K_j^T
+        mbar_wait(&kv_full[s], ph);
+        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int nb = 0; nb < ND; ++nb) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma_bf16(tmem_S, umma_desc_k_sw128(aQ + nb * (kTileQ * 128)) + 2 * k,
+                        umma_desc_k_sw128(aK + nb * (kTileK * 128)) + 2 * k, idesc_s, (nb | k) != 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(s_full);
+        // ---- T = P_j V_j
+        mbar_wait(p_full, j & 1);
+        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int nb = 0; nb < ND; ++nb) {
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k) {
+            // A = P: K-major, keys [16k, 16k+16) live in block k/4 (16 KB each), 32 B per 16 keys inside the atom
+            const uint64_t da = umma_desc_k_sw128(aP + (k >> 2) * (kTileQ * 128)) + 2 * (k & 3);
+            // B = V: MN-major, 16 keys = 16 rows of 128 B
+            const uint64_t db = umma_desc_mn_sw128(aV + nb * (kTileK * 128) + k * 16 * 128, kTileK * 128);
+            tc_mma_bf16(tmem_T + nb * 64, da, db, idesc_pv, k != 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(o_full);
+        tc_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // =============================== softmax / output: one thread per query row ===============================
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    float O[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) O[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    uint8_t* prow = sP + r * 128;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kvalid = p.Tk - j * kTileK;           // keys of this tile that exist
+      // ---- pass 1: running max (log2 domain)
+      float mx = m;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sv = (c * 32 + i < kvalid) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
+          mx = fmaxf(mx, sv);
+        }
+      }
+      const float alpha = exp2_approx(m - mx);         // m = -inf on the first tile -> 0
+      // ---- fold the previous tile's P V into the running output, then rescale
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_T + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        mbar_arrive(o_empty);
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) O[i] *= alpha;
+      l *= alpha;
+      // ---- pass 2: P = exp2(s - max) -> bf16 -> shared memory (K-major SW128), row sum
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k0 = c * 32 + 2 * i;
+          const float p0 = (k0 < kvalid) ? exp2_approx(__uint_as_float(v[2 * i]) * p.scale_log2 - mx) : 0.f;
+          const float p1 = (k0 + 1 < kvalid) ? exp2_approx(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - mx) : 0.f;
+          l += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        // 32 keys = 4 chunks of 16 B; key block (c >> 1) of 64 keys, chunk index (c & 1) * 4 + q inside the row
+        uint8_t* blk = prow + (c >> 1) * (kTileQ * 128);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
+          *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      m = mx;
+    }
+    // ---- last tile's P V, normalise, store
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_T + lane_off + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+    }
+    const int q = q0 + r;
+    if (q < p.Tq) {
+      const float inv = 1.f / l;
+      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D;
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) {
+        uint4 o;
+        o.x = pack_bf16(O[8 * i] * inv, O[8 * i + 1] * inv);
+        o.y = pack_bf16(O[8 * i + 2] * inv, O[8 * i + 3] * inv);
+        o.z = pack_bf16(O[8 * i + 4] * inv, O[8 * i + 5] * inv);
+        o.w = pack_bf16(O[8 * i + 6] * inv, O[8 * i + 7] * inv);
+        reinterpret_cast<uint4*>(op)[i] = o;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <int D>
+static int launch_attention(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                            dim3 grid, cudaStream_t stream) {
+  constexpr int smem = kTileQ * D * 2 + 2 * 2 * kTileK * D * 2 + kTileQ * kTileK * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention)");
+    configured = true;
+  }
+  attention_kernel<D><<<grid, 192, smem, stream>>>(p, mq, mk, mv);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention launch");
+}
+
+static int make_qkv_map(CUtensorMap* m, const void* ptr, int width, int64_t ld, int64_t bs, int tokens, int batch) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(tokens), static_cast<uint64_t>(batch)};
+  const uint64_t str[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(batch > 1 ? bs : ld * tokens) * 2};
+  const uint32_t box[3] = {64u, 128u, 1u};
+  const uint32_t es[3] = {1u, 1u, 1u};
+  return encode_tensor_map(m, const_cast<void*>(ptr), 3, dims, str, box, es);
+}
+
+}  // namespace ur
+
+using namespace ur;
+
+extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void* k, int64_t ldk, int64_t k_bs,
+                            const void* v, int64_t ldv, int64_t v_bs, void* out, int64_t ldo, int64_t out_bs, int batch,
+                            int heads, int head_dim, int tq, int tk, int kv_shared, float scale, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!q || !k || !v || !out) return set_error(UR_ERR_ARG, "ur_attention: null pointer");
+  if (head_dim != 64 && head_dim != 128) return set_error(UR_ERR_ARG, "ur_attention: head_dim must be 64 or 128");
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_bs % 8 || k_bs % 8 || v_bs % 8 || out_bs % 8 ||
+      ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+        reinterpret_cast<uintptr_t>(out)) & 15))
+    return set_error(UR_ERR_ARG, "ur_attention: pitches must be multiples of 8 elements and pointers 16-byte aligned");
+  if (batch <= 0 || heads <= 0 || tq <= 0 || tk <= 0) return set_error(UR_ERR_ARG, "ur_attention: bad sizes");
+  const int width = heads * head_dim;
+  CUtensorMap mq, mk, mv;
+  int rc = make_qkv_map(&mq, q, width, ldq, q_bs, tq, batch);
+  if (rc) return rc;
+  const int kvb = kv_shared ? 1 : batch;
+  rc = make_qkv_map(&mk, k, width, ldk, k_bs, tk, kvb);
+  if (rc) return rc;
+  rc = make_qkv_map(&mv, v, width, ldv, v_bs, tk, kvb);
+  if (rc) return rc;
+  AttnParams p;
+  p.Tq = tq;
+  p.Tk = tk;
+  p.heads = heads;
+  p.kv_shared = kv_shared;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out = static_cast<bf16*>(out);
+  p.ldo = ldo;
+  p.out_bs = out_bs;
+  dim3 grid((tq + kTileQ - 1) / kTileQ, heads, batch);
+  return head_dim == 64 ? launch_attention<64>(p, mq, mk, mv, grid, stream)
+                        : launch_attention<128>(p, mq, mk, mv, grid, stream);
+}

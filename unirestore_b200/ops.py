@@ -248,7 +248,27 @@ def transpose_tokens(x, tokens_pad=None):
 def attention(q, k, v, heads, out=None):
     """softmax(q k^T / sqrt(d)) v per head.  q [B,Tq,C], k/v [B or 1,Tk,C] bf16 (channel-slice views ok).
 
-    Unfused v1 path: per head S = QK^T (ur_conv_gemm, fp32) -> ur_softmax_rows -> O = P V^T (ur_conv_gemm)."""
+    head_dim 64 / 128: one launch of the fused tcgen05 flash-attention kernel; other head dims (the VAE's single
+    512-wide head) take the unfused GEMM -> softmax -> GEMM path."""
+    B, Tq, Cc = q.shape
+    d = Cc // heads
+    if d not in (64, 128):
+        return attention_unfused(q, k, v, heads, out)
+    Tk = k.shape[1]
+    shared = k.shape[0] == 1 and B > 1
+    if out is None:
+        out = torch.empty((B, Tq, Cc), device=q.device, dtype=torch.bfloat16)
+    for t in (q, k, v, out):
+        if t.dtype != torch.bfloat16 or t.stride(-1) != 1:
+            raise ValueError("attention operands must be bf16 with unit channel stride")
+    check(_lib().ur_attention(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(v), v.stride(1),
+                              v.stride(0), _ptr(out), out.stride(1), out.stride(0), B, heads, d, Tq, Tk, int(shared),
+                              float(d) ** -0.5, _stream()), "ur_attention")
+    return out
+
+
+def attention_unfused(q, k, v, heads, out=None):
+    """Per head S = QK^T (ur_conv_gemm, fp32) -> ur_softmax_rows -> O = P V^T (ur_conv_gemm)."""
     B, Tq, Cc = q.shape
     Tk = k.shape[1]
     d = Cc // heads
