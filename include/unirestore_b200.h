@@ -93,6 +93,8 @@ typedef struct ur_conv_desc {
 int ur_conv_gemm(const ur_conv_desc* desc_host, void* stream);
 /* N tile the auto heuristic picks for (n, m_tiles); weight packers for gated acts must use it. */
 int ur_conv_gemm_pick_bn(int n, int gated);
+/* Development switch (A/B timing): 1 routes every call to the non-persistent kernel; returns the previous value. */
+int ur_debug_force_gemm_v1(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (HBM-bound, bf16 channels-last, 128-bit vectorised)

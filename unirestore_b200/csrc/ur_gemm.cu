@@ -13,39 +13,11 @@
 //
 // Reference arithmetic implemented: every nn.Conv2d / nn.Linear on the UniRestore hot path
 // (see include/unirestore_b200.h for the call-site list).
-#include "ur_common.cuh"
-#include "ur_host.h"
+#include "ur_gemm.h"
+
+#include <stdlib.h>
 
 namespace ur {
-
-struct GemmParams {
-  int B, Ho, Wo, N;
-  int cblocks;         // 64-channel blocks per tap
-  int c1;              // channels of source 1 (k-blocks with c >= c1 read source 2)
-  int kc;              // K extent per tap in the packed weights
-  int ntaps, stride;
-  unsigned long long dy_pack, dx_pack;  // 4 bits per tap, value+8
-  int wt_log2, ht_log2;                 // M tile = Wt x Ht x Bt pixels, Wt*Ht*Bt = 128
-  int tiles_x, tiles_y;
-  int group_kc, group_nc;
-  int w_batched;
-  void* out;
-  int out_f32;
-  long long out_sb, out_sy, out_sx;
-  float alpha;
-  const float* bias;
-  const float* rowvec;
-  long long rowvec_sb;
-  const float* chscale;
-  long long chscale_sb;
-  const bf16* residual;
-  long long res_sb, res_sy, res_sx;
-  int act;
-};
-
-constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 
 template <int BN>
 __host__ __device__ constexpr int tmem_cols() {
@@ -288,9 +260,17 @@ static int launch_conv_gemm(const GemmParams& p, const CUtensorMap& a1, const CU
 
 using namespace ur;
 
+static int g_force_v1 = getenv("UR_GEMM_V1") != nullptr;
+// development switch: 1 = route every ur_conv_gemm call to the one-tile-per-CTA kernel
+extern "C" int ur_debug_force_gemm_v1(int on) {
+  const int old = g_force_v1;
+  g_force_v1 = on;
+  return old;
+}
+
 extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
-  if (gated) {
-    if (n % 160 == 0) return 160;
+  if (gated) {   // M-independent (weights are packed for it); half tiles must be multiples of 32 columns
+    if (n % 256 == 0) return 256;
     if (n % 128 == 0) return 128;
     return n % 64 == 0 ? 64 : 0;
   }
@@ -300,6 +280,31 @@ extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
   if (n <= 64) return 64;
   if (n % 64 == 0 && n < 256) return 64;
   return 128;
+}
+
+// N tile for a plain (non-gated) GEMM given the number of M tiles: the largest exact divisor of n that still
+// yields at least one tile per SM; otherwise the candidate with the least padded work.
+static int pick_bn_auto(int n, long long m_tiles) {
+  const int cands[4] = {256, 160, 128, 64};
+  int exact_small = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (n % bn) continue;
+    exact_small = bn;
+    if (m_tiles * (n / bn) >= num_sms()) return bn;
+  }
+  if (exact_small) return exact_small;
+  int best = 64;
+  long long best_pad = -1;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const long long pad = static_cast<long long>((n + bn - 1) / bn) * bn;
+    if (best_pad < 0 || pad < best_pad) {
+      best_pad = pad;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
@@ -313,15 +318,6 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     return set_error(UR_ERR_ARG, "ur_conv_gemm: bad ntaps / stride");
   if (d->n <= 0) return set_error(UR_ERR_ARG, "ur_conv_gemm: n must be positive");
   const bool gated = d->act == UR_ACT_GEGLU || d->act == UR_ACT_GATE;
-  int bn = d->bn ? d->bn : ur_conv_gemm_pick_bn(d->n, gated);
-  if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
-  if (gated && (d->n % bn)) return set_error(UR_ERR_ARG, "ur_conv_gemm: gated act needs n %% bn == 0");
-  int kc = ctot;
-  if (d->group_kc) {
-    if (d->group_kc % 64 || d->group_nc % bn || d->c2)
-      return set_error(UR_ERR_ARG, "ur_conv_gemm: grouped conv needs group_kc %% 64 == 0, group_nc %% bn == 0");
-    kc = d->group_kc;
-  }
   if ((reinterpret_cast<uintptr_t>(d->x1) | reinterpret_cast<uintptr_t>(d->x2) | reinterpret_cast<uintptr_t>(d->w)) & 15)
     return set_error(UR_ERR_ARG, "ur_conv_gemm: pointers must be 16-byte aligned");
 
@@ -342,6 +338,16 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   }
   if (best_cost < 0) return set_error(UR_ERR_ARG, "ur_conv_gemm: no tile shape");
   const int Wt = 1 << best_w, Ht = 1 << best_h, Bt = 128 >> (best_w + best_h);
+
+  int bn = d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : pick_bn_auto(d->n, best_cost));
+  if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
+  if (gated && (d->n % bn)) return set_error(UR_ERR_ARG, "ur_conv_gemm: gated act needs n %% bn == 0");
+  int kc = ctot;
+  if (d->group_kc) {
+    if (d->group_kc % 64 || d->group_nc % bn || d->c2)
+      return set_error(UR_ERR_ARG, "ur_conv_gemm: grouped conv needs group_kc %% 64 == 0, group_nc %% bn == 0");
+    kc = d->group_kc;
+  }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -419,6 +425,22 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     const uint32_t estr[3] = {1u, 1u, 1u};
     int rc = encode_tensor_map(&mW, const_cast<void*>(d->w), 3, dims, str, box, estr);
     if (rc) return rc;
+  }
+
+  // ---- fast path: persistent kernel with TMA-store epilogue (bf16 output, 16-byte aligned pitches)
+  const int n_out = gated ? d->n / 2 : d->n;
+  const bool force_v1 = g_force_v1 != 0;
+  const bool out_ok = d->out_dtype == UR_DT_BF16 && !(reinterpret_cast<uintptr_t>(d->out) & 15) && d->out_sx % 8 == 0 &&
+                      d->out_sy % 8 == 0 && d->out_sb % 8 == 0 && n_out % 8 == 0;
+  const bool res_ok = !d->residual || (!(reinterpret_cast<uintptr_t>(d->residual) & 15) && d->res_sx % 8 == 0 &&
+                                       d->res_sy % 8 == 0 && d->res_sb % 8 == 0);
+  const bool vec_ok = (!d->rowvec || d->rowvec_sb == 0 || Bt == 1) && (!d->chscale || d->chscale_sb == 0 || Bt == 1);
+  if (!force_v1 && out_ok && res_ok && vec_ok && (!gated || bn % 64 == 0)) {
+    const CUtensorMap& mOut = mA1;   // (TMA-store epilogue retired: narrow boxes were slower than coalesced stores)
+    const int n_tiles = (d->n + bn - 1) / bn;
+    const long long total = static_cast<long long>(n_tiles) * p.tiles_x * p.tiles_y * tiles_b;
+    if (total > 0x7fffffffLL) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many tiles");
+    return launch_conv_gemm_persistent(p, mA1, mA2, mW, mOut, bn, static_cast<int>(total), n_tiles, stream);
   }
 
   dim3 grid((d->n + bn - 1) / bn, p.tiles_x * p.tiles_y * tiles_b, 1);

@@ -1,0 +1,42 @@
+// Shared between the two implicit-GEMM kernels (ur_gemm.cu: one tile per CTA, direct-store epilogue, any output
+// type / alignment; ur_gemm_persistent.cu: persistent, TMEM double-buffered, TMA-store epilogue).
+#pragma once
+#include "ur_common.cuh"
+#include "ur_host.h"
+
+namespace ur {
+
+struct GemmParams {
+  int B, Ho, Wo, N;
+  int cblocks;         // 64-channel blocks per tap
+  int c1;              // channels of source 1 (k-blocks with c >= c1 read source 2)
+  int kc;              // K extent per tap in the packed weights
+  int ntaps, stride;
+  unsigned long long dy_pack, dx_pack;  // 4 bits per tap, value+8
+  int wt_log2, ht_log2;                 // M tile = Wt x Ht x Bt pixels, Wt*Ht*Bt = 128
+  int tiles_x, tiles_y;
+  int group_kc, group_nc;
+  int w_batched;
+  void* out;
+  int out_f32;
+  long long out_sb, out_sy, out_sx;
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  long long rowvec_sb;
+  const float* chscale;
+  long long chscale_sb;
+  const bf16* residual;
+  long long res_sb, res_sy, res_sx;
+  int act;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+
+// persistent kernel entry (ur_gemm_persistent.cu); mOut: 64B-swizzled 4-D map of the bf16 output, box (32, Wt, Ht, Bt)
+int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
+                                const CUtensorMap& out, int bn, int total_tiles, int n_tiles, cudaStream_t stream);
+
+}  // namespace ur

@@ -40,7 +40,7 @@ static int resolve_encode() {
 }
 
 int encode_tensor_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, const uint32_t* elem_strides) {
+                      const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
   int rc = resolve_encode();
   if (rc) return rc;
   cuuint64_t gd[5], gs[5];
@@ -52,7 +52,10 @@ int encode_tensor_map(CUtensorMap* map, void* base, int rank, const uint64_t* di
     if (i < rank - 1) gs[i] = strides_bytes[i];
   }
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), base, gd, gs, bx, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return set_error(UR_ERR_CUDA,

@@ -14,6 +14,6 @@ int set_error(int code, const char* fmt, ...);
 int set_cuda_error(cudaError_t e, const char* what);
 // bf16 tiled tensor map with 128-byte swizzle and zero OOB fill.
 int encode_tensor_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, const uint32_t* elem_strides);
+                      const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes = 128);
 int num_sms();
 }  // namespace ur

@@ -7,6 +7,8 @@ The leftover FLOPs probe and unconditional ``raise`` at unifie.py:43-53 are not 
 stay on the GPU in bf16 channels-last; latents / noise / scheduler state are fp32; timesteps and the DDIM index
 math are host-side integers (bit-exact with the reference tables).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -37,6 +39,10 @@ class DiffUIE(nn.Module):
             self.scheduler = DDIMScheduler.from_pretrained("stabilityai/sd-turbo", subfolder="scheduler")
             self.scheduler.set_timesteps(cnet["num_inference_steps"], device=self.train_timesteps.device)
         self._temb_cache = {}
+        # CUDA-graph replay of the whole forward for static shapes (one capture per (shape, task, noise-mode));
+        # every kernel behind the C-ABI is capture-safe (no allocation, no synchronisation).
+        self.use_cuda_graph = os.environ.get("UNIRESTORE_CUDA_GRAPH", "0") == "1"
+        self._graphs = {}
 
     # ---------------------------------------------------------------------------------- training-time helpers
     def diffuse(self, latents, timesteps=None, noise=None):                      # unifie.py:77-89
@@ -67,6 +73,7 @@ class DiffUIE(nn.Module):
 
     def clear_caches(self):
         self._temb_cache = {}
+        self._graphs = {}
         for m in self.modules():
             if hasattr(m, "invalidate"):
                 m.invalidate()
@@ -103,6 +110,18 @@ class DiffUIE(nn.Module):
     def forward(self, images, task, noise=None):
         """images fp32 [B,3,H,W] in [0,1] -> restored fp32 [B,3,H,W].  ``noise=(posterior, diffuse)`` injects the two
         RNG draws of the reference (autoencoder.py:152, unifie.py:87) for parity runs."""
+        if self.use_cuda_graph and images.is_cuda:
+            return self._forward_graphed(images, task, noise)
+        return self._forward_impl(images, task, noise)
+
+    def _forward_graphed(self, images, task, noise):
+        key = (tuple(images.shape), task, noise is not None, str(images.device))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = _GraphedForward(self, images, task, noise)
+        return g(images, noise)
+
+    def _forward_impl(self, images, task, noise=None):
         org_h, org_w = images.shape[-2:]
         h, w = org_h, org_w
         images = images.float()
@@ -119,3 +138,30 @@ class DiffUIE(nn.Module):
         if (h, w) != (org_h, org_w):                                             # unifie.py:165-168
             preds = F.interpolate(preds, (org_h, org_w), mode="bicubic", align_corners=False, antialias=False)
         return preds
+
+
+class _GraphedForward:
+    """One captured CUDA graph of ``DiffUIE._forward_impl`` for fixed input shapes; inputs are copied into static
+    buffers, the graph is replayed, the static output is cloned."""
+
+    def __init__(self, model, images, task, noise):
+        self.img = images.detach().float().clone()
+        self.noise = tuple(n.detach().float().clone() for n in noise) if noise is not None else None
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                    # warm-up: weight packing, caches, function attributes
+            for _ in range(2):
+                model._forward_impl(self.img, task, self.noise)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = model._forward_impl(self.img, task, self.noise)
+
+    def __call__(self, images, noise):
+        self.img.copy_(images, non_blocking=True)
+        if self.noise is not None:
+            for dst, src in zip(self.noise, noise):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out.clone()
