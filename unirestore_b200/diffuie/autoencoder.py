@@ -20,6 +20,11 @@ CFRM_STACKS = ((128, 1), (256, 1), (512, 9))                      # autoencoder.
 TFA_SPECS = ((512, 512, False), (512, 256, False), (512, 128, True))   # autoencoder.py:122-126
 
 
+class UnknownTaskError(KeyError, AttributeError):
+    """``task_prompts[task]`` of an unregistered task (autoencoder.py:47): nn.ParameterDict raises AttributeError on the
+    reference's torch, KeyError by the mapping protocol -- callers catching either keep working."""
+
+
 class _Stack(nn.Sequential):
     def run(self, x):
         for m in self:
@@ -83,7 +88,7 @@ class SkipConnectedAutoEncoder(nn.Module):
         prompt = None
         if self.tedit_type:
             if task not in dec.task_prompts:                                 # `task_prompts[task]` (autoencoder.py:47)
-                raise KeyError(task)
+                raise UnknownTaskError(task)
             prompt = dec.task_prompts[task]
         _, z8 = ops.latent_axpby(latents.float().contiguous(), 1.0, want_out=False, want_nhwc8=True,
                                  scale8=1.0 / float(self.vae.config["scaling_factor"]))          # autoencoder.py:170

@@ -154,9 +154,12 @@ class _GraphedForward:
                 model._forward_impl(self.img, task, self.noise)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from .. import _cabi
+        n0 = _cabi.launch_count
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = model._forward_impl(self.img, task, self.noise)
+        self.n_launches = _cabi.launch_count - n0          # C-ABI kernel launches recorded in the graph
 
     def __call__(self, images, noise):
         self.img.copy_(images, non_blocking=True)
