@@ -95,6 +95,8 @@ int ur_conv_gemm(const ur_conv_desc* desc_host, void* stream);
 int ur_conv_gemm_pick_bn(int n, int gated);
 /* Development switch (A/B timing): 1 routes every call to the non-persistent kernel; returns the previous value. */
 int ur_debug_force_gemm_v1(int on);
+/* Development: device buffer of 128 int64 that receives per-role clock64 timestamps of CTA 0 (NULL = off). */
+int ur_debug_set_gemm_trace(void* buf);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (HBM-bound, bf16 channels-last, 128-bit vectorised)

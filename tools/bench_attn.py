@@ -1,0 +1,37 @@
+"""Micro-benchmark of ur_attention (CUDA events)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unirestore_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--cases", default="self64,self32,cross64,ctrl64")
+a = ap.parse_args()
+CASES = {"self64": (8, 5, 64, 4096, 4096), "self32": (8, 10, 64, 1024, 1024), "cross64": (8, 5, 64, 4096, 77),
+         "ctrl64": (8, 4, 64, 4096, 4096), "self16": (8, 20, 64, 256, 256)}
+dev = "cuda:0"
+for name in a.cases.split(","):
+    B, h, d, Tq, Tk = CASES[name]
+    C = h * d
+    q = torch.randn(B, Tq, C, device=dev).to(torch.bfloat16)
+    kb = 1 if Tk == 77 else B
+    k = torch.randn(kb, Tk, C, device=dev).to(torch.bfloat16)
+    v = torch.randn(kb, Tk, C, device=dev).to(torch.bfloat16)
+    out = torch.empty_like(q)
+    for _ in range(3):
+        ops.attention(q, k, v, h, out=out)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(a.iters):
+        ops.attention(q, k, v, h, out=out)
+    e.record()
+    torch.cuda.synchronize()
+    t = s.elapsed_time(e) * 1e-3 / a.iters
+    fl = 4.0 * B * Tq * Tk * C
+    print("%-8s B=%d h=%d d=%d Tq=%d Tk=%d  %8.1f us  %7.1f TF/s" % (name, B, h, d, Tq, Tk, t * 1e6, fl / t / 1e12), flush=True)

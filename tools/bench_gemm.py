@@ -8,18 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from unirestore_b200 import ops  # noqa: E402
 
-SHAPES = {  # name: (B, H, W, Cin, Cout, taps)
-    "unet_c3_320_64": (8, 64, 64, 320, 320, 9),
-    "unet_c3_640_32": (8, 32, 32, 640, 640, 9),
-    "unet_c3_1280_16": (8, 16, 16, 1280, 1280, 9),
-    "unet_c3_1280_8": (8, 8, 8, 1280, 1280, 9),
-    "vae_c3_128_512": (8, 512, 512, 128, 128, 9),
-    "vae_c3_256_256": (8, 256, 256, 256, 256, 9),
-    "vae_c3_512_128": (8, 128, 128, 512, 512, 9),
-    "lin_320_320_4096": (8, 1, 4096, 320, 320, 1),
-    "lin_320_2560_4096": (8, 1, 4096, 320, 2560, 1),
-    "lin_1280_1280_256": (8, 1, 256, 1280, 1280, 1),
-}
+from tools.bench_gemm_shapes import SHAPES  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--shapes", default=",".join(SHAPES))
 ap.add_argument("--iters", type=int, default=10)

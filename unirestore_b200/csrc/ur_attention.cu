@@ -168,52 +168,87 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int kvalid = p.Tk - j * kTileK;           // keys of this tile that exist
-      // ---- pass 1: running max (log2 domain)
-      float mx = m;
+      const bool full_tile = kvalid >= kTileK;         // warp-uniform: only the last tile needs key masking
+      // ---- pass 1: row max of the raw scores (scale > 0 is applied afterwards); two TMEM loads in flight
+      float raw = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t va[32], vb[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, va);
+        tmem_ld32(tmem_S + lane_off + (c + 1) * 32, vb);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sv = (c * 32 + i < kvalid) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-          mx = fmaxf(mx, sv);
+          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i < kvalid) raw = fmaxf(raw, __uint_as_float(va[i]));
+            if ((c + 1) * 32 + i < kvalid) raw = fmaxf(raw, __uint_as_float(vb[i]));
+          }
         }
       }
+      const float mx = fmaxf(m, raw * p.scale_log2);   // log2 domain
       const float alpha = exp2_approx(m - mx);         // m = -inf on the first tile -> 0
-      // ---- fold the previous tile's P V into the running output, then rescale
+      // ---- fold the previous tile's P V into the running output (O = O * alpha + T)
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tmem_T + lane_off + c * 32, v);
+        uint32_t t0[32];
+        tmem_ld32(tmem_T + lane_off, t0);
+        if constexpr (D == 64) {
+          uint32_t t1[32];
+          tmem_ld32(tmem_T + lane_off + 32, t1);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) {
+            O[i] = (O[i] + __uint_as_float(t0[i])) * alpha;
+            O[32 + i] = (O[32 + i] + __uint_as_float(t1[i])) * alpha;
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) O[i] = (O[i] + __uint_as_float(t0[i])) * alpha;
+#pragma unroll
+          for (int c = 1; c < D / 32; ++c) {
+            tmem_ld32(tmem_T + lane_off + c * 32, t0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) O[c * 32 + i] = (O[c * 32 + i] + __uint_as_float(t0[i])) * alpha;
+          }
         }
         tc_fence_before();
         mbar_arrive(o_empty);
       }
-#pragma unroll
-      for (int i = 0; i < D; ++i) O[i] *= alpha;
       l *= alpha;
-      // ---- pass 2: P = exp2(s - max) -> bf16 -> shared memory (K-major SW128), row sum
+      // ---- pass 2: P = exp2(s * scale - max) -> bf16 -> shared memory (K-major SW128), row sum
+      const float nmx = -mx;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_S + lane_off + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int k0 = c * 32 + 2 * i;
-          const float p0 = (k0 < kvalid) ? exp2_approx(__uint_as_float(v[2 * i]) * p.scale_log2 - mx) : 0.f;
-          const float p1 = (k0 + 1 < kvalid) ? exp2_approx(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - mx) : 0.f;
-          l += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = exp2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, nmx));
+            const float p1 = exp2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, nmx));
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k0 = c * 32 + 2 * i;
+            const float p0 = (k0 < kvalid) ? exp2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, nmx)) : 0.f;
+            const float p1 = (k0 + 1 < kvalid) ? exp2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, nmx)) : 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
         }
         // 32 keys = 4 chunks of 16 B; key block (c >> 1) of 64 keys, chunk index (c & 1) * 4 + q inside the row
         uint8_t* blk = prow + (c >> 1) * (kTileQ * 128);
@@ -223,6 +258,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
           *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
         }
       }
+      l += l0 + l1;
       tc_fence_before();
       mbar_arrive(s_empty);
       fence_proxy_async_smem();

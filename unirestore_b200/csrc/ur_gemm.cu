@@ -261,6 +261,12 @@ static int launch_conv_gemm(const GemmParams& p, const CUtensorMap& a1, const CU
 using namespace ur;
 
 static int g_force_v1 = getenv("UR_GEMM_V1") != nullptr;
+static long long* g_trace = nullptr;
+// development: device buffer of 128 int64 receiving per-role clock64 timestamps of CTA 0 (nullptr = off)
+extern "C" int ur_debug_set_gemm_trace(void* buf) {
+  g_trace = static_cast<long long*>(buf);
+  return 0;
+}
 // development switch: 1 = route every ur_conv_gemm call to the one-tile-per-CTA kernel
 extern "C" int ur_debug_force_gemm_v1(int on) {
   const int old = g_force_v1;
@@ -282,25 +288,21 @@ extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
   return 128;
 }
 
-// N tile for a plain (non-gated) GEMM given the number of M tiles: the largest exact divisor of n that still
-// yields at least one tile per SM; otherwise the candidate with the least padded work.
+// N tile for a plain (non-gated) GEMM given the number of M tiles: minimise (rounds over the SMs) x (per-tile
+// k-block time).  The main loop is shared-memory-bandwidth bound (TMA write + UMMA read of A 16 KB + W bn*128 B),
+// i.e. time per k-block ~ (128 + bn); padded columns of a non-dividing bn count as waste through the tile count.
 static int pick_bn_auto(int n, long long m_tiles) {
   const int cands[4] = {256, 160, 128, 64};
-  int exact_small = 0;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    if (n % bn) continue;
-    exact_small = bn;
-    if (m_tiles * (n / bn) >= num_sms()) return bn;
-  }
-  if (exact_small) return exact_small;
   int best = 64;
-  long long best_pad = -1;
+  double best_cost = -1.0;
+  const int sms = num_sms();
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
-    const long long pad = static_cast<long long>((n + bn - 1) / bn) * bn;
-    if (best_pad < 0 || pad < best_pad) {
-      best_pad = pad;
+    const long long tiles = m_tiles * ((n + bn - 1) / bn);
+    const long long rounds = (tiles + sms - 1) / sms;
+    const double cost = static_cast<double>(rounds) * (128.0 + bn);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
       best = bn;
     }
   }
@@ -390,6 +392,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   p.res_sy = d->res_sy;
   p.res_sx = d->res_sx;
   p.act = d->act;
+  p.trace = g_trace;
 
   // ---- tensor maps
   CUtensorMap mA1, mA2, mW;

@@ -29,6 +29,7 @@ struct GemmParams {
   const bf16* residual;
   long long res_sb, res_sy, res_sx;
   int act;
+  long long* trace;   // development: per-role clock64 timestamps of CTA 0 (nullptr = off)
 };
 
 constexpr int kBlockM = 128;

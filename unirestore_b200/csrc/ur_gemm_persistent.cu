@@ -1,13 +1,17 @@
 // Persistent implicit-GEMM convolution / linear kernel (the fast path of ur_conv_gemm).
 //
 //   one CTA per SM, static round-robin over the (m_tile, n_tile) list (n fastest, so CTAs running side by side
-//   share the activation tile in L2);  192 threads:
-//     warp 0      TMA producer        smem ring of STAGES x (A 128x64 bf16 + W BNx64 bf16), 128-byte swizzle
-//     warp 1      tcgen05.mma issuer  accumulators double-buffered in TMEM (2 x BN fp32 columns): the epilogue of
-//                                     tile i overlaps the main loop of tile i+1
-//     warps 2..5  epilogue            tcgen05.ld (32 columns per load) -> +bias/+temb (staged in smem) -> activation
-//                                     -> channel scale -> +residual -> bf16 -> smem staging (64-byte swizzle)
-//                                     -> TMA store (coalesced, clipped at the tensor edge by the hardware)
+//   share the activation tile in L2);  14 warps:
+//     warps 0..2  activation (A) TMA producers, k-block kb is issued by warp kb % 3   } a single thread issuing every
+//     warps 3..4  weight (W) TMA producers,     k-block kb is issued by warp 3 + kb%2 } TMA costs ~700 cycles per
+//                 k-block (the 4-D tiled load alone ~390) and starves the tensor core, hence the fan-out
+//     warp  5     TMEM allocator + single-thread tcgen05.mma issuer; accumulators double-buffered in TMEM
+//                 (2 x BN fp32 columns): the epilogue of tile i overlaps the main loop of tile i+1
+//     warps 6..13 epilogue, two warp groups of 128 threads; group g owns the 32-column sub-blocks g, g+2, ...
+//                 tcgen05.ld -> +bias/+temb (staged in smem) -> activation / GEGLU / gate -> channel scale
+//                 -> +residual -> bf16 -> padded smem tile -> coalesced 16-byte global stores (8 rows x 64 B per
+//                 warp instruction instead of 32 scattered rows)
+//   smem ring of STAGES x (A 128x64 bf16 + W BNx64 bf16), 128-byte swizzle, full/empty mbarriers.
 //
 // Same arithmetic and operand layout as ur_gemm.cu (see there / include/unirestore_b200.h for the reference
 // call sites); this variant requires a bf16 output whose pitches are multiples of 8 elements.
@@ -15,40 +19,51 @@
 
 namespace ur {
 
-constexpr int kStagePitch = 144;                 // 64 bf16 + 16 B pad: conflict-free row-wise 16-byte accesses
-constexpr int kStagingBytes = kBlockM * kStagePitch;
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+constexpr int kEpiPitch = 80;                        // 32 bf16 + 16 B pad: conflict-free row-wise 16-byte writes
+constexpr int kEpiStageBytes = kBlockM * kEpiPitch;  // per epilogue warp group
+constexpr int kNumAProd = 3, kNumWProd = 2;
+constexpr int kMmaWarp = kNumAProd + kNumWProd;      // 5
+constexpr int kEpiWarp0 = kMmaWarp + 1;              // 6
+constexpr int kThreads = (kEpiWarp0 + 8) * 32;       // 448
 
 template <int BN>
 __host__ __device__ constexpr int pstages() {
   return BN == 256 ? 4 : (BN == 160 ? 5 : (BN == 128 ? 6 : 8));
 }
 
+struct TileCoord {
+  int n0, x0, y0, b0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t, int n_tiles, int BN, int Wt, int Ht, int Bt) {
+  TileCoord c;
+  const int nt = t % n_tiles;
+  int mt = t / n_tiles;
+  c.n0 = nt * BN;
+  const int tx = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  const int ty = mt % p.tiles_y;
+  const int tb = mt / p.tiles_y;
+  c.x0 = tx * Wt;
+  c.y0 = ty * Ht;
+  c.b0 = tb * Bt;
+  return c;
+}
+
+__device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
 template <int BN>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap mapA1,
                             const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW,
-                            const __grid_constant__ CUtensorMap mapOut, int total_tiles, int n_tiles) {
+                            int total_tiles, int n_tiles) {
   constexpr int STAGES = pstages<BN>();
   constexpr int kWBytes = BN * kBlockK * 2;
   constexpr int kStageBytes = kABytes + kWBytes;
   constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* staging = smem + STAGES * kStageBytes;                       // 128 x 144 B
-  float* s_add = reinterpret_cast<float*>(staging + kStagingBytes);      // [2][BN]
-  float* s_mul = s_add + 2 * BN;                                         // [2][BN]
+  uint8_t* staging = smem + STAGES * kStageBytes;                          // [2 groups][128 x 80 B]
+  float* s_add = reinterpret_cast<float*>(staging + 2 * kEpiStageBytes);    // [2][BN]
+  float* s_mul = s_add + 2 * BN;                                            // [2][BN]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_mul + 2 * BN);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
@@ -60,12 +75,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   const int Wt = 1 << p.wt_log2, Ht = 1 << p.ht_log2;
   const int Bt = kBlockM >> (p.wt_log2 + p.ht_log2);
   const int nkb = p.ntaps * p.cblocks;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  if (tracing && threadIdx.x == 0) p.trace[7 * 16] = clock64();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapW);
-    tma_prefetch_desc(&mapOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -76,7 +92,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -84,38 +100,33 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tracing && threadIdx.x == 0) p.trace[7 * 16 + 1] = clock64();
 
-  if (warp == 0) {
-    // =============================== TMA producer ===============================
+  if (warp < kNumAProd) {
+    // =============================== activation TMA producers ===============================
     if (lane == 0) {
-      int kiter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = t % n_tiles;
-        int mt = t / n_tiles;
-        const int n0 = nt * BN;
-        const int tx = mt % p.tiles_x;
-        mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int tb = mt / p.tiles_y;
-        const int x0 = tx * Wt, y0 = ty * Ht, b0 = tb * Bt;
-        const int cbase = p.group_kc ? (n0 / p.group_nc) * p.group_kc : 0;
-        const int wb = p.w_batched ? b0 : 0;
+      int kiter = 0, it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt);
+        const int cbase = p.group_kc ? (tc.n0 / p.group_nc) * p.group_kc : 0;
+        if (tracing && warp == 0 && it < 8) p.trace[0 * 16 + it] = clock64();
         int tap = 0, cb = 0;
         for (int kb = 0; kb < nkb; ++kb, ++kiter) {
-          const int s = kiter % STAGES;
-          const uint32_t ph = (kiter / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&full_bar[s], kStageBytes);
-          uint8_t* sa = smem + s * kStageBytes;
-          const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
-          const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
-          const int c = cbase + cb * kBlockK;
-          const int xi = x0 * p.stride + dx, yi = y0 * p.stride + dy;
-          if (c < p.c1)
-            tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, b0);
-          else
-            tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, b0);
-          tma_load_3d(sa + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, n0, wb);
+          if (kiter % kNumAProd == warp) {
+            const int s = kiter % STAGES;
+            const uint32_t ph = (kiter / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_expect_tx(&full_bar[s], kStageBytes);     // covers the W bytes issued by the weight producer
+            const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
+            const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
+            const int c = cbase + cb * kBlockK;
+            const int xi = tc.x0 * p.stride + dx, yi = tc.y0 * p.stride + dy;
+            uint8_t* sa = smem + s * kStageBytes;
+            if (c < p.c1)
+              tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, tc.b0);
+            else
+              tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, tc.b0);
+          }
           if (++cb == p.cblocks) {
             cb = 0;
             ++tap;
@@ -123,7 +134,30 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp < kMmaWarp) {
+    // =============================== weight TMA producers ===============================
+    if (lane == 0) {
+      const int me = warp - kNumAProd;
+      int kiter = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt);
+        const int wb = p.w_batched ? tc.b0 : 0;
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++kiter) {
+          if (kiter % kNumWProd == me) {
+            const int s = kiter % STAGES;
+            const uint32_t ph = (kiter / STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            tma_load_3d(smem + s * kStageBytes + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, tc.n0, wb);
+          }
+          if (++cb == p.cblocks) {
+            cb = 0;
+            ++tap;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
@@ -133,10 +167,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
+        if (tracing && it < 8) p.trace[1 * 16 + it] = clock64();
         for (int kb = 0; kb < nkb; ++kb, ++kiter) {
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
+          if (tracing && it < 8 && kb == 0) p.trace[2 * 16 + it] = clock64();
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint64_t da = umma_desc_k_sw128(sa);
@@ -146,176 +182,183 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           tc_commit(&empty_bar[s]);
         }
         tc_commit(&tfull_bar[as]);
+        if (tracing && it < 8) p.trace[3 * 16 + it] = clock64();
       }
     }
   } else {
     // =============================== epilogue ===============================
-    // 8 warps: two per TMEM lane quarter; warp group g = (warp - 2) / 4 handles the 32-column sub-blocks
-    // g, g + 2, g + 4, ...  Each thread finishes 32 columns of ITS row (TMEM lane) entirely in registers and
-    // writes 64 contiguous bytes; the residual of the next sub-block is prefetched while the current one is
-    // being processed.  No shared-memory staging, no intra-tile barriers.
-    const int q = warp & 3;
-    const int grp = (warp - 2) >> 2;             // 0 or 1
-    const int r = q * 32 + lane;                 // tile row = TMEM lane
-    const int et = threadIdx.x - 64;             // 0..255
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int grp = (warp - kEpiWarp0) >> 2;      // warp group 0 / 1
+    const int r = q * 32 + lane;                  // tile row = TMEM lane
+    const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+    const int gt = et & 127;                      // thread index inside the warp group
     const bool gated = p.act == UR_ACT_GEGLU || p.act == UR_ACT_GATE;
     const int n_out = gated ? (p.N >> 1) : p.N;
     const int ncols = gated ? (BN >> 1) : BN;
-    const int xl = r & (Wt - 1);
-    const int yl = (r >> p.wt_log2) & (Ht - 1);
-    const int bl = r >> (p.wt_log2 + p.ht_log2);
     const bool has_mul = p.chscale != nullptr;
-    const bool has_alpha = p.alpha != 1.0f;
+    const bool plain = !gated && p.act == UR_ACT_NONE && !has_mul && p.alpha == 1.0f;
+    // cooperative phase: thread gt moves 16-byte chunk (gt & 3) of rows (gt >> 2) + 32 i, i = 0..3
+    const int cchunk = gt & 3;
+    const int crow0 = gt >> 2;
+    uint8_t* stg = staging + grp * kEpiStageBytes;
+    uint8_t* srow = stg + r * kEpiPitch;
     bf16* outp = reinterpret_cast<bf16*>(p.out);
+    float a_nx = 0.f, m_nx = 1.f;                 // this thread's column of the NEXT tile's add / mul vectors
+    auto fetch_vec = [&](int tt) {
+      const TileCoord tn = tile_coord(p, tt, n_tiles, BN, Wt, Ht, Bt);
+      const int n = tn.n0 + et;
+      const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
+      float a = 0.f;
+      if (n < p.N) {
+        if (p.bias) a += __ldg(p.bias + n);
+        if (p.rowvec) a += __ldg(p.rowvec + tn.b0 * p.rowvec_sb + n);
+      }
+      a_nx = a;
+      m_nx = (has_mul && et < ncols && no0 + et < n_out) ? __ldg(p.chscale + tn.b0 * p.chscale_sb + no0 + et) : 1.f;
+    };
+    if (et < BN && static_cast<int>(blockIdx.x) < total_tiles) fetch_vec(blockIdx.x);
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const int nt = t % n_tiles;
-      int mt = t / n_tiles;
-      const int n0 = nt * BN;
-      const int tx = mt % p.tiles_x;
-      mt /= p.tiles_x;
-      const int ty = mt % p.tiles_y;
-      const int tb = mt / p.tiles_y;
-      const int x0 = tx * Wt, y0 = ty * Ht, b0 = tb * Bt;
-      const int nout0 = gated ? (n0 >> 1) : n0;
+      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt);
+      const int nout0 = gated ? (tc.n0 >> 1) : tc.n0;
       const int as = it & 1;
-      // ---- stage the per-column add / mul vectors of this tile (double-buffered by `as`)
+      // ---- stage the per-column add / mul vectors of this tile (double-buffered by `as`); the values were
+      //      fetched one tile ahead so their global-load latency hides behind the previous tile's epilogue
       float* add = s_add + as * BN;
       float* mul = s_mul + as * BN;
       if (et < BN) {
-        const int c = et;
-        const int n = n0 + c;
-        float a = 0.f;
-        if (n < p.N) {
-          if (p.bias) a += __ldg(p.bias + n);
-          if (p.rowvec) a += __ldg(p.rowvec + b0 * p.rowvec_sb + n);
-        }
-        add[c] = a;
-        float m = 1.f;
-        if (has_mul && c < ncols && nout0 + c < n_out) m = __ldg(p.chscale + b0 * p.chscale_sb + nout0 + c);
-        mul[c] = m;
+        add[et] = a_nx;
+        mul[et] = m_nx;
+        const int tn = t + gridDim.x;
+        if (tn < total_tiles) fetch_vec(tn);
       }
-      const int x = x0 + xl, y = y0 + yl, b = b0 + bl;
-      const bool row_ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-      bf16* orow = outp + b * p.out_sb + y * p.out_sy + x * p.out_sx + nout0;
-      const bf16* rrow = (p.residual && row_ok) ? p.residual + b * p.res_sb + y * p.res_sy + x * p.res_sx + nout0 : nullptr;
-      // residual prefetch of this warp group's first sub-block
-      uint4 rv[4];
-      int c = grp * 32;
-      if (rrow != nullptr && c < ncols && nout0 + c + 32 <= n_out) {
+      // global element offsets of the 4 rows this thread moves in the cooperative phases (-1: outside the tensor)
+      long long coff[4], roff[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rv[j] = __ldg(reinterpret_cast<const uint4*>(rrow + c) + j);
+      for (int i = 0; i < 4; ++i) {
+        const int rr = crow0 + 32 * i;
+        const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
+        const int b = tc.b0 + (rr >> (p.wt_log2 + p.ht_log2));
+        const bool ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+        coff[i] = ok ? (b * p.out_sb + y * p.out_sy + x * p.out_sx + nout0) : -1;
+        roff[i] = ok ? (b * p.res_sb + y * p.res_sy + x * p.res_sx + nout0) : -1;
+      }
+      // residual of this group's first sub-block, fetched (coalesced) while the main loop still runs
+      uint4 rres[4];
+      int c = grp * 32;
+      if (p.residual) {
+        const int col = c + cchunk * 8;
+        const bool okc = c < ncols && nout0 + col + 8 <= n_out;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          rres[i] = (okc && roff[i] >= 0) ? __ldg(reinterpret_cast<const uint4*>(p.residual + roff[i] + col))
+                                           : make_uint4(0u, 0u, 0u, 0u);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tracing && it < 8 && et == 0) p.trace[4 * 16 + it] = clock64();
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      if (tracing && it < 8 && et == 0) p.trace[5 * 16 + it] = clock64();
       tc_fence_after();
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
       for (; c < ncols; c += 64) {
-        uint32_t va[32], vg[32];
+        uint32_t va[32];
         tmem_ld32(trow + c, va);
-        if (gated) tmem_ld32(trow + (BN >> 1) + c, vg);
-        // prefetch the residual of the next sub-block of this warp group
-        uint4 rn[4];
-        const int cn = c + 64;
-        const bool pre = rrow != nullptr && cn < ncols && nout0 + cn + 32 <= n_out;
-        if (pre) {
+        // (A) staging tile is free again; park the prefetched residual chunk in it
+        group_barrier(2 + grp);
+        if (p.residual) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rn[j] = __ldg(reinterpret_cast<const uint4*>(rrow + cn) + j);
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(stg + (crow0 + 32 * i) * kEpiPitch + cchunk * 16) = rres[i];
+          group_barrier(4 + grp);
+          // prefetch the residual of this group's next sub-block
+          const int cn = c + 64;
+          const int col = cn + cchunk * 8;
+          const bool okc = cn < ncols && nout0 + col + 8 <= n_out;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rres[i] = (okc && roff[i] >= 0) ? __ldg(reinterpret_cast<const uint4*>(p.residual + roff[i] + col))
+                                             : make_uint4(0u, 0u, 0u, 0u);
         }
-        tmem_ld_wait();
-        const bool full = nout0 + c + 32 <= n_out;
-        uint32_t o[16];
+        float f[32];
+        if (plain) {
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 ad = *reinterpret_cast<const float4*>(add + c + 4 * j);
-          float f[4] = {__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]), __uint_as_float(va[4 * j + 2]),
-                        __uint_as_float(va[4 * j + 3])};
-          if (has_alpha) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] *= p.alpha;
+          for (int j = 0; j < 8; ++j) {
+            const float4 ad = *reinterpret_cast<const float4*>(add + c + 4 * j);
+            f[4 * j] = __uint_as_float(va[4 * j]) + ad.x;
+            f[4 * j + 1] = __uint_as_float(va[4 * j + 1]) + ad.y;
+            f[4 * j + 2] = __uint_as_float(va[4 * j + 2]) + ad.z;
+            f[4 * j + 3] = __uint_as_float(va[4 * j + 3]) + ad.w;
           }
-          f[0] += ad.x;
-          f[1] += ad.y;
-          f[2] += ad.z;
-          f[3] += ad.w;
-          if (gated) {
-            const float4 ag = *reinterpret_cast<const float4*>(add + (BN >> 1) + c + 4 * j);
-            float g[4] = {__uint_as_float(vg[4 * j]), __uint_as_float(vg[4 * j + 1]), __uint_as_float(vg[4 * j + 2]),
-                          __uint_as_float(vg[4 * j + 3])};
-            if (has_alpha) {
+        } else {
+          uint32_t vg[32];
+          if (gated) tmem_ld32(trow + (BN >> 1) + c, vg);
+          tmem_ld_wait();
 #pragma unroll
-              for (int k = 0; k < 4; ++k) g[k] *= p.alpha;
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(va[j]) * p.alpha + add[c + j];
+            if (gated) {
+              const float g = __uint_as_float(vg[j]) * p.alpha + add[(BN >> 1) + c + j];
+              v = (p.act == UR_ACT_GEGLU) ? v * gelu_erf_f(g) : v * g;
+            } else if (p.act == UR_ACT_SILU) {
+              v = silu_f(v);
+            } else if (p.act == UR_ACT_GELU) {
+              v = gelu_erf_f(v);
             }
-            g[0] += ag.x;
-            g[1] += ag.y;
-            g[2] += ag.z;
-            g[3] += ag.w;
-            if (p.act == UR_ACT_GEGLU) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) f[k] *= gelu_erf_f(g[k]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) f[k] *= g[k];
-            }
-          } else if (p.act == UR_ACT_SILU) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] = silu_f(f[k]);
-          } else if (p.act == UR_ACT_GELU) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] = gelu_erf_f(f[k]);
+            f[j] = has_mul ? v * mul[c + j] : v;
           }
-          if (has_mul) {
-            const float4 mu = *reinterpret_cast<const float4*>(mul + c + 4 * j);
-            f[0] *= mu.x;
-            f[1] *= mu.y;
-            f[2] *= mu.z;
-            f[3] *= mu.w;
-          }
-          if (rrow != nullptr && full) {
-            const uint4 rq = rv[j >> 1];
-            const uint32_t u0 = (j & 1) ? rq.z : rq.x, u1 = (j & 1) ? rq.w : rq.y;
-            float a0, a1;
-            unpack_bf16(u0, a0, a1);
-            f[0] += a0;
-            f[1] += a1;
-            unpack_bf16(u1, a0, a1);
-            f[2] += a0;
-            f[3] += a1;
-          }
-          o[2 * j] = pack_bf16(f[0], f[1]);
-          o[2 * j + 1] = pack_bf16(f[2], f[3]);
         }
-        if (row_ok) {
-          if (full) {
+        // own row: (+ residual) -> bf16 -> staging
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              reinterpret_cast<uint4*>(orow + c)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          } else {                                  // ragged tail of the channel dimension (n_out % 32 != 0)
-            for (int j = 0; j < 32; ++j) {
-              if (nout0 + c + j < n_out) {
-                float lo, hi;
-                unpack_bf16(o[j >> 1], lo, hi);
-                float v = (j & 1) ? hi : lo;
-                if (rrow != nullptr) v += __bfloat162float(rrow[c + j]);
-                orow[c + j] = __float2bfloat16(v);
+        for (int j = 0; j < 4; ++j) {
+          uint4* sp = reinterpret_cast<uint4*>(srow + j * 16);
+          if (p.residual) {
+            const uint4 rv = *sp;
+            const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float a0, a1;
+              unpack_bf16(u[k], a0, a1);
+              f[8 * j + 2 * k] += a0;
+              f[8 * j + 2 * k + 1] += a1;
+            }
+          }
+          *sp = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                           pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+        }
+        group_barrier(6 + grp);
+        // (C) coalesced write-out: a warp stores 8 rows x 64 contiguous bytes per instruction
+        {
+          const int col = c + cchunk * 8;
+          if (nout0 + col + 8 <= n_out) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (coff[i] >= 0)
+                *reinterpret_cast<uint4*>(outp + coff[i] + col) =
+                    *reinterpret_cast<const uint4*>(stg + (crow0 + 32 * i) * kEpiPitch + cchunk * 16);
+            }
+          } else if (nout0 + col < n_out) {               // ragged channel tail (n_out % 8 != 0 never reaches here)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (coff[i] >= 0) {
+                const bf16* sv = reinterpret_cast<const bf16*>(stg + (crow0 + 32 * i) * kEpiPitch + cchunk * 16);
+                for (int k = 0; k < 8; ++k)
+                  if (nout0 + col + k < n_out) outp[coff[i] + col + k] = sv[k];
               }
             }
           }
         }
-        if (pre) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rv[j] = rn[j];
-        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
+      if (tracing && it < 8 && et == 0) p.trace[6 * 16 + it] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -323,8 +366,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
 
 template <int BN>
 static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                    const CUtensorMap& out, int total_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = pstages<BN>() * (kABytes + BN * kBlockK * 2) + kStagingBytes + 4 * BN * 4 + 512;
+                    int total_tiles, int n_tiles, cudaStream_t stream) {
+  constexpr int smem = pstages<BN>() * (kABytes + BN * kBlockK * 2) + 2 * kEpiStageBytes + 4 * BN * 4 + 512;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -332,18 +376,18 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_gemm_persistent_kernel<BN><<<grid, 320, smem, stream>>>(p, a1, a2, w, out, total_tiles, n_tiles);
+  conv_gemm_persistent_kernel<BN><<<grid, kThreads, smem, stream>>>(p, a1, a2, w, total_tiles, n_tiles);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "conv_gemm_persistent launch");
 }
 
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                                const CUtensorMap& out, int bn, int total_tiles, int n_tiles, cudaStream_t stream) {
+                                const CUtensorMap& /*unused*/, int bn, int total_tiles, int n_tiles, cudaStream_t stream) {
   switch (bn) {
-    case 64: return launch_p<64>(p, a1, a2, w, out, total_tiles, n_tiles, stream);
-    case 128: return launch_p<128>(p, a1, a2, w, out, total_tiles, n_tiles, stream);
-    case 160: return launch_p<160>(p, a1, a2, w, out, total_tiles, n_tiles, stream);
-    default: return launch_p<256>(p, a1, a2, w, out, total_tiles, n_tiles, stream);
+    case 64: return launch_p<64>(p, a1, a2, w, total_tiles, n_tiles, stream);
+    case 128: return launch_p<128>(p, a1, a2, w, total_tiles, n_tiles, stream);
+    case 160: return launch_p<160>(p, a1, a2, w, total_tiles, n_tiles, stream);
+    default: return launch_p<256>(p, a1, a2, w, total_tiles, n_tiles, stream);
   }
 }
 

@@ -134,7 +134,14 @@ class ResnetBlock2D(UrModule):
         h = ops.group_norm(x, self.groups, p["g1"], p["b1"], self.eps, silu=True, x2=x2)
         tvec = None
         if temb is not None and self.time_emb_proj is not None:
-            tvec = ops.small_linear(temb, p["wt"], p["tb"], act_in="silu")
+            # time_emb_proj(silu(temb)) only depends on the (cached, per-timestep) embedding tensor: computed once
+            cache = p.setdefault("tvec", {})
+            hit = cache.get(id(temb))
+            if hit is None or hit[0] is not temb:
+                if len(cache) > 64:
+                    cache.clear()
+                hit = cache[id(temb)] = (temb, ops.small_linear(temb, p["wt"], p["tb"], act_in="silu"))
+            tvec = hit[1]
         h = ops.conv_gemm(h, p["w1"], co, taps=TAPS_3x3, bias=p["c1b"], rowvec=tvec)
         h = ops.group_norm(h, self.groups, p["g2"], p["b2"], self.eps, silu=True)
         if self.conv_shortcut is not None:
