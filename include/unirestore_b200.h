@@ -97,6 +97,7 @@ int ur_conv_gemm_pick_bn(int n, int gated);
 int ur_debug_force_gemm_v1(int on);
 /* Development: device buffer of 128 int64 that receives per-role clock64 timestamps of CTA 0 (NULL = off). */
 int ur_debug_set_gemm_trace(void* buf);
+int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (HBM-bound, bf16 channels-last, 128-bit vectorised)

@@ -26,13 +26,14 @@ struct AttnParams {
   float scale_log2;       // softmax scale * log2(e)
   bf16* out;
   long long ldo, out_bs;
+  long long* trace;       // development: clock64 timestamps of CTA (0,0,0), softmax thread 0 and the MMA thread
 };
 
 constexpr int kTileQ = 128;
 constexpr int kTileK = 128;
 
 template <int D>
-__global__ void __launch_bounds__(192, D == 64 ? 2 : 1)
+__global__ void __launch_bounds__(320, D == 64 ? 2 : 1)
 attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
                  const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
   constexpr int ND = D / 64;                       // 64-column blocks per head
@@ -54,6 +55,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
   uint64_t* o_full = p_full + 1;
   uint64_t* o_empty = o_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  int* xch = reinterpret_cast<int*>(tmem_slot + 2);       // [128] running row max (order-preserving int key) shared by the two half-row threads
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTileQ;
@@ -71,10 +73,10 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_empty, 256);
+    mbar_init(p_full, 256);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    mbar_init(o_empty, 256);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -115,15 +117,12 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
+      // S_j = Q K_j^T into TMEM columns [0,128); K_j lives in stage j % kStages
+      auto issue_s = [&](int j) {
         const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        const uint32_t aK = smem_u32(sKV + s * 2 * kKBytes);
-        const uint32_t aV = aK + kKBytes;
-        // ---- S = Q K_j^T
-        mbar_wait(&kv_full[s], ph);
-        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        mbar_wait(&kv_full[s], (j / kStages) & 1);
         tc_fence_after();
+        const uint32_t aK = smem_u32(sKV + s * 2 * kKBytes);
 #pragma unroll
         for (int nb = 0; nb < ND; ++nb) {
 #pragma unroll
@@ -133,9 +132,23 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
           }
         }
         tc_commit(s_full);
-        // ---- T = P_j V_j
+      };
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j % kStages;
+        const uint32_t aV = smem_u32(sKV + s * 2 * kKBytes) + kKBytes;
+        const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 4 && j < 8;
+        if (trm) p.trace[32 + (j - 4) * 8 + 0] = clock64();
+        // P_j is in shared memory and S_j has been consumed: S_{j+1} goes first so that the softmax warps can start
+        // on it while P_j V_j is still being issued / executed
         mbar_wait(p_full, j & 1);
+        mbar_wait(s_empty, j & 1);
+        if (trm) p.trace[32 + (j - 4) * 8 + 1] = clock64();
+        if (j + 1 < nkv) issue_s(j + 1);
+        if (trm) p.trace[32 + (j - 4) * 8 + 2] = clock64();
+        // ---- T = P_j V_j
         if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+        if (trm) p.trace[32 + (j - 4) * 8 + 3] = clock64();
         tc_fence_after();
 #pragma unroll
         for (int nb = 0; nb < ND; ++nb) {
@@ -150,84 +163,88 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
         }
         tc_commit(o_full);
         tc_commit(&kv_empty[s]);
+        if (trm) p.trace[32 + (j - 4) * 8 + 4] = clock64();
       }
     }
   } else {
-    // =============================== softmax / output: one thread per query row ===============================
+    // =============================== softmax / output: TWO threads per query row ===============================
+    // Warps 2..9: warp w and w+4 share a TMEM lane quarter; thread (row r, half hf) owns score columns
+    // [64 hf, 64 hf + 64) of its row and output columns [D/2 hf, D/2 hf + D/2).  The row maximum is exchanged through
+    // shared memory once per KV tile; the row sum is kept as two partial sums and combined at the end.
+    constexpr int DH = D / 2;
     const int qd = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-    float O[D];
+    const uint32_t tS = tmem_S + lane_off + hf * 64;
+    const uint32_t tT = tmem_T + lane_off + hf * DH;
+    float O[DH];
 #pragma unroll
-    for (int i = 0; i < D; ++i) O[i] = 0.f;
+    for (int i = 0; i < DH; ++i) O[i] = 0.f;
     float m = -INFINITY, l = 0.f;
     const uint32_t swz = static_cast<uint32_t>(r & 7);
-    uint8_t* prow = sP + r * 128;
+    uint8_t* prow = sP + hf * (kTileQ * 128) + r * 128;        // key block hf (64 keys) of the P tile, row r
+    int* my_x = xch + r;
+    // order-preserving float <-> int key so that one shared atomicMax keeps the RUNNING row maximum of both halves
+    auto f2key = [](float f) { const int b = __float_as_int(f); return b >= 0 ? b : (b ^ 0x7fffffff); };
+    auto key2f = [](int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); };
+    if (hf == 0) *my_x = f2key(-INFINITY);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 
     for (int j = 0; j < nkv; ++j) {
+      const bool trs = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0 && hf == 0 && j >= 4 && j < 8;
+      if (trs) p.trace[(j - 4) * 8 + 0] = clock64();
       mbar_wait(s_full, j & 1);
+      if (trs) p.trace[(j - 4) * 8 + 1] = clock64();
       tc_fence_after();
-      const int kvalid = p.Tk - j * kTileK;           // keys of this tile that exist
-      const bool full_tile = kvalid >= kTileK;         // warp-uniform: only the last tile needs key masking
-      // ---- pass 1: row max of the raw scores (scale > 0 is applied afterwards); two TMEM loads in flight
+      const int kvalid = p.Tk - j * kTileK - hf * 64;   // keys of this thread's 64-column half that exist
+      const bool full_tile = kvalid >= 64;               // warp-uniform: only the last tile needs key masking
+      // ---- pass 1: partial row max of the raw scores (scale > 0 is applied afterwards)
       float raw = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        uint32_t va[32], vb[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, va);
-        tmem_ld32(tmem_S + lane_off + (c + 1) * 32, vb);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
         if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, fmaxf(__uint_as_float(va[i]), __uint_as_float(vb[i])));
+          for (int i = 0; i < 32; ++i) raw = fmaxf(raw, __uint_as_float(v[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i < kvalid) raw = fmaxf(raw, __uint_as_float(va[i]));
-            if ((c + 1) * 32 + i < kvalid) raw = fmaxf(raw, __uint_as_float(vb[i]));
-          }
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < kvalid) raw = fmaxf(raw, __uint_as_float(v[i]));
         }
       }
-      const float mx = fmaxf(m, raw * p.scale_log2);   // log2 domain
+      atomicMax(my_x, f2key(raw));
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float mx = key2f(*my_x) * p.scale_log2;    // running max over all tiles so far, log2 domain (>= m)
       const float alpha = exp2_approx(m - mx);         // m = -inf on the first tile -> 0
-      // ---- fold the previous tile's P V into the running output (O = O * alpha + T)
+      if (trs) p.trace[(j - 4) * 8 + 2] = clock64();
+      // ---- fold the previous tile's P V into the running output (O = (O + T) * alpha)
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
+        if (trs) p.trace[(j - 4) * 8 + 3] = clock64();
         tc_fence_after();
-        uint32_t t0[32];
-        tmem_ld32(tmem_T + lane_off, t0);
-        if constexpr (D == 64) {
-          uint32_t t1[32];
-          tmem_ld32(tmem_T + lane_off + 32, t1);
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t t0[32];
+          tmem_ld32(tT + c * 32, t0);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            O[i] = (O[i] + __uint_as_float(t0[i])) * alpha;
-            O[32 + i] = (O[32 + i] + __uint_as_float(t1[i])) * alpha;
-          }
-        } else {
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) O[i] = (O[i] + __uint_as_float(t0[i])) * alpha;
-#pragma unroll
-          for (int c = 1; c < D / 32; ++c) {
-            tmem_ld32(tmem_T + lane_off + c * 32, t0);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) O[c * 32 + i] = (O[c * 32 + i] + __uint_as_float(t0[i])) * alpha;
-          }
+          for (int i = 0; i < 32; ++i) O[c * 32 + i] = (O[c * 32 + i] + __uint_as_float(t0[i])) * alpha;
         }
         tc_fence_before();
         mbar_arrive(o_empty);
       }
       l *= alpha;
-      // ---- pass 2: P = exp2(s * scale - max) -> bf16 -> shared memory (K-major SW128), row sum
+      if (trs) p.trace[(j - 4) * 8 + 4] = clock64();
+      // ---- pass 2: P = exp2(s * scale - max) -> bf16 -> shared memory (K-major SW128), partial row sum
       const float nmx = -mx;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
+        tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
         uint32_t pk[16];
         if (full_tile) {
@@ -250,38 +267,49 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
             pk[i] = pack_bf16(p0, p1);
           }
         }
-        // 32 keys = 4 chunks of 16 B; key block (c >> 1) of 64 keys, chunk index (c & 1) * 4 + q inside the row
-        uint8_t* blk = prow + (c >> 1) * (kTileQ * 128);
+        // 32 keys = 4 chunks of 16 B at chunk index c * 4 + q of the 128-byte row (128-byte swizzle)
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
-          *reinterpret_cast<uint4*>(blk + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+          const uint32_t chunk = static_cast<uint32_t>(c * 4 + qq) ^ swz;
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
         }
       }
       l += l0 + l1;
+      if (trs) p.trace[(j - 4) * 8 + 5] = clock64();
       tc_fence_before();
       mbar_arrive(s_empty);
       fence_proxy_async_smem();
       mbar_arrive(p_full);
+      if (trs) p.trace[(j - 4) * 8 + 6] = clock64();
       m = mx;
     }
-    // ---- last tile's P V, normalise, store
+    // ---- last tile's P V, combine the two partial row sums, normalise, store
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_T + lane_off + c * 32, v);
+    for (int c = 0; c < DH / 32; ++c) {
+      uint32_t t0[32];
+      tmem_ld32(tT + c * 32, t0);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(t0[i]);
     }
+    // combine the two partial row sums through the same slot (two rounds: hf 0 publishes, hf 1 adds and publishes)
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) *my_x = __float_as_int(l);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 1) {
+      l += __int_as_float(*my_x);
+      *my_x = __float_as_int(l);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (hf == 0) l = __int_as_float(*my_x);
     const int q = q0 + r;
     if (q < p.Tq) {
       const float inv = 1.f / l;
-      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D;
+      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D + hf * DH;
 #pragma unroll
-      for (int i = 0; i < D / 8; ++i) {
+      for (int i = 0; i < DH / 8; ++i) {
         uint4 o;
         o.x = pack_bf16(O[8 * i] * inv, O[8 * i + 1] * inv);
         o.y = pack_bf16(O[8 * i + 2] * inv, O[8 * i + 3] * inv);
@@ -303,14 +331,14 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
 template <int D>
 static int launch_attention(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                             dim3 grid, cudaStream_t stream) {
-  constexpr int smem = kTileQ * D * 2 + 2 * 2 * kTileK * D * 2 + kTileQ * kTileK * 2 + 256;
+  constexpr int smem = kTileQ * D * 2 + 2 * 2 * kTileK * D * 2 + kTileQ * kTileK * 2 + 640;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention)");
     configured = true;
   }
-  attention_kernel<D><<<grid, 192, smem, stream>>>(p, mq, mk, mv);
+  attention_kernel<D><<<grid, 320, smem, stream>>>(p, mq, mk, mv);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention launch");
 }
@@ -326,6 +354,13 @@ static int make_qkv_map(CUtensorMap* m, const void* ptr, int width, int64_t ld, 
 }  // namespace ur
 
 using namespace ur;
+
+static long long* g_attn_trace = nullptr;
+// development: device buffer of 64 int64 receiving clock64 timestamps (nullptr = off)
+extern "C" int ur_debug_set_attention_trace(void* buf) {
+  g_attn_trace = static_cast<long long*>(buf);
+  return 0;
+}
 
 extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void* k, int64_t ldk, int64_t k_bs,
                             const void* v, int64_t ldv, int64_t v_bs, void* out, int64_t ldo, int64_t out_bs, int batch,
@@ -356,6 +391,7 @@ extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void
   p.out = static_cast<bf16*>(out);
   p.ldo = ldo;
   p.out_bs = out_bs;
+  p.trace = g_attn_trace;
   dim3 grid((tq + kTileQ - 1) / kTileQ, heads, batch);
   return head_dim == 64 ? launch_attention<64>(p, mq, mk, mv, grid, stream)
                         : launch_attention<128>(p, mq, mk, mv, grid, stream);
