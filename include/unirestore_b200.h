@@ -97,6 +97,8 @@ int ur_conv_gemm_pick_bn(int n, int gated);
 int ur_debug_force_gemm_v1(int on);
 /* Development: device buffer of 128 int64 that receives per-role clock64 timestamps of CTA 0 (NULL = off). */
 int ur_debug_set_gemm_trace(void* buf);
+/* Development: CTA-pair (tcgen05 cta_group::2) GEMM tiles: -1 auto (cost model), 0 never, 1 whenever legal. */
+int ur_debug_set_gemm_pair_mode(int mode);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 
 /* ------------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ SIGNATURES = {
     "ur_conv_gemm_pick_bn": (C.c_int, [C.c_int, C.c_int]),
     "ur_debug_force_gemm_v1": (C.c_int, [C.c_int]),
     "ur_debug_set_gemm_trace": (C.c_int, [_P]),
+    "ur_debug_set_gemm_pair_mode": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_trace": (C.c_int, [_P]),
     "ur_chan_stats": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _I, _I, _P]),
     "ur_norm_apply": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _I64,

@@ -15,6 +15,7 @@
 // (see include/unirestore_b200.h for the call-site list).
 #include "ur_gemm.h"
 
+#include <math.h>
 #include <stdlib.h>
 
 namespace ur {
@@ -288,25 +289,52 @@ extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
   return 128;
 }
 
-// N tile for a plain (non-gated) GEMM given the number of M tiles: minimise (rounds over the SMs) x (per-tile
-// k-block time).  The main loop is shared-memory-bandwidth bound (TMA write + UMMA read of A 16 KB + W bn*128 B),
-// i.e. time per k-block ~ (128 + bn); padded columns of a non-dividing bn count as waste through the tile count.
-static int pick_bn_auto(int n, long long m_tiles) {
+// Tile configuration (N tile, single CTA vs CTA pair) minimising (rounds over the SMs) x (time per k-block).
+// Measured model of the main loop (cycles per 64-deep k-block): the UMMA itself 2*bn (128 rows per SM), the
+// shared-memory traffic of TMA write + UMMA read, (16 KB + W bytes) * 2 / 128 B per cycle, and ~75 cycles of issue
+// per tcgen05.mma.  A pair stages only bn/2 weight rows per CTA.
+static int g_pair_mode = getenv("UR_GEMM_PAIR") ? atoi(getenv("UR_GEMM_PAIR")) : -1;   // -1 auto, 0 never, 1 whenever legal
+extern "C" int ur_debug_set_gemm_pair_mode(int mode) {
+  const int old = g_pair_mode;
+  g_pair_mode = mode;
+  return old;
+}
+
+static void pick_tile_config(int n, long long m_tiles, int fixed_bn, bool pair_legal, int* bn_out, bool* pair_out) {
   const int cands[4] = {256, 160, 128, 64};
-  int best = 64;
-  double best_cost = -1.0;
   const int sms = num_sms();
+  double best_cost = -1.0;
+  int best_bn = fixed_bn ? fixed_bn : 64;
+  bool best_pair = false;
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
-    const long long tiles = m_tiles * ((n + bn - 1) / bn);
-    const long long rounds = (tiles + sms - 1) / sms;
-    const double cost = static_cast<double>(rounds) * (128.0 + bn);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+    if (fixed_bn && bn != fixed_bn) continue;
+    const long long n_tiles = (n + bn - 1) / bn;
+    for (int pair = 0; pair < 2; ++pair) {
+      if (pair && (!pair_legal || g_pair_mode == 0)) continue;
+      if (!pair && pair_legal && g_pair_mode == 1) continue;
+      // Measured on B200 (tools/bench_gemm.py, round 1): pairs win only with full 256-wide N tiles and many waves
+      // (VAE 256/512-channel convs at 128^2..256^2: +9..16 %); they lose 3..15 % on the UNet's 2-4 wave problems
+      // and on 128/160-wide tiles, so auto mode keeps those on single CTAs.
+      if (pair && g_pair_mode < 0 && !(bn == 256 && n % 256 == 0 && m_tiles >= 8LL * sms)) continue;
+      double t, rounds;
+      if (pair) {
+        t = fmax(fmax(2.0 * bn, 256.0 + bn), 300.0);
+        rounds = static_cast<double>(((m_tiles + 1) / 2 * n_tiles + sms / 2 - 1) / (sms / 2));
+      } else {
+        t = fmax(256.0 + 2.0 * bn, 300.0);
+        rounds = static_cast<double>((m_tiles * n_tiles + sms - 1) / sms);
+      }
+      const double cost = rounds * t;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_bn = bn;
+        best_pair = pair != 0;
+      }
     }
   }
-  return best;
+  *bn_out = best_bn;
+  *pair_out = best_pair;
 }
 
 extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
@@ -341,7 +369,10 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   if (best_cost < 0) return set_error(UR_ERR_ARG, "ur_conv_gemm: no tile shape");
   const int Wt = 1 << best_w, Ht = 1 << best_h, Bt = 128 >> (best_w + best_h);
 
-  int bn = d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : pick_bn_auto(d->n, best_cost));
+  int bn = 0;
+  bool pair = false;
+  pick_tile_config(d->n, best_cost, d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : 0),
+                   !d->w_batched && best_cost >= 2, &bn, &pair);
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
   if (gated && (d->n % bn)) return set_error(UR_ERR_ARG, "ur_conv_gemm: gated act needs n %% bn == 0");
   int kc = ctot;
@@ -394,6 +425,17 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   p.act = d->act;
   p.trace = g_trace;
 
+  // ---- fast path (persistent kernel): bf16 output with 16-byte aligned pitches
+  const int n_out = gated ? d->n / 2 : d->n;
+  const bool force_v1 = g_force_v1 != 0;
+  const bool out_ok = d->out_dtype == UR_DT_BF16 && !(reinterpret_cast<uintptr_t>(d->out) & 15) && d->out_sx % 8 == 0 &&
+                      d->out_sy % 8 == 0 && d->out_sb % 8 == 0 && n_out % 8 == 0;
+  const bool res_ok = !d->residual || (!(reinterpret_cast<uintptr_t>(d->residual) & 15) && d->res_sx % 8 == 0 &&
+                                       d->res_sy % 8 == 0 && d->res_sb % 8 == 0);
+  const bool vec_ok = (!d->rowvec || d->rowvec_sb == 0 || Bt == 1) && (!d->chscale || d->chscale_sb == 0 || Bt == 1);
+  const bool fast_path = !force_v1 && out_ok && res_ok && vec_ok && (!gated || bn % 64 == 0);
+  const bool pair_path = fast_path && pair;
+
   // ---- tensor maps
   CUtensorMap mA1, mA2, mW;
   const uint32_t s = static_cast<uint32_t>(d->stride);
@@ -424,26 +466,18 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     const uint64_t wbs = d->w_bs ? static_cast<uint64_t>(d->w_bs) : wld * d->n;
     if (wld % 8 || wbs % 8) return set_error(UR_ERR_ARG, "ur_conv_gemm: weight pitches must be multiples of 8");
     const uint64_t str[2] = {wld * 2, wbs * 2};
-    const uint32_t box[3] = {64u, static_cast<uint32_t>(bn), 1u};
+    const uint32_t box[3] = {64u, static_cast<uint32_t>(pair_path ? bn / 2 : bn), 1u};
     const uint32_t estr[3] = {1u, 1u, 1u};
     int rc = encode_tensor_map(&mW, const_cast<void*>(d->w), 3, dims, str, box, estr);
     if (rc) return rc;
   }
 
-  // ---- fast path: persistent kernel with TMA-store epilogue (bf16 output, 16-byte aligned pitches)
-  const int n_out = gated ? d->n / 2 : d->n;
-  const bool force_v1 = g_force_v1 != 0;
-  const bool out_ok = d->out_dtype == UR_DT_BF16 && !(reinterpret_cast<uintptr_t>(d->out) & 15) && d->out_sx % 8 == 0 &&
-                      d->out_sy % 8 == 0 && d->out_sb % 8 == 0 && n_out % 8 == 0;
-  const bool res_ok = !d->residual || (!(reinterpret_cast<uintptr_t>(d->residual) & 15) && d->res_sx % 8 == 0 &&
-                                       d->res_sy % 8 == 0 && d->res_sb % 8 == 0);
-  const bool vec_ok = (!d->rowvec || d->rowvec_sb == 0 || Bt == 1) && (!d->chscale || d->chscale_sb == 0 || Bt == 1);
-  if (!force_v1 && out_ok && res_ok && vec_ok && (!gated || bn % 64 == 0)) {
-    const CUtensorMap& mOut = mA1;   // (TMA-store epilogue retired: narrow boxes were slower than coalesced stores)
+  if (fast_path) {
     const int n_tiles = (d->n + bn - 1) / bn;
-    const long long total = static_cast<long long>(n_tiles) * p.tiles_x * p.tiles_y * tiles_b;
+    const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * tiles_b;
+    const long long total = static_cast<long long>(n_tiles) * (pair_path ? (m_tiles + 1) / 2 : m_tiles);
     if (total > 0x7fffffffLL) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many tiles");
-    return launch_conv_gemm_persistent(p, mA1, mA2, mW, mOut, bn, static_cast<int>(total), n_tiles, stream);
+    return launch_conv_gemm_persistent(p, mA1, mA2, mW, pair_path, bn, static_cast<int>(total), n_tiles, stream);
   }
 
   dim3 grid((d->n + bn - 1) / bn, p.tiles_x * p.tiles_y * tiles_b, 1);

@@ -36,8 +36,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 
-// persistent kernel entry (ur_gemm_persistent.cu); mOut: 64B-swizzled 4-D map of the bf16 output, box (32, Wt, Ht, Bt)
+// persistent kernel entry (ur_gemm_persistent.cu).  pair = true: CTA pairs with tcgen05.mma.cta_group::2 on 256 x bn
+// tiles (w: tensor map with bn/2-row boxes, total_units = pair tiles); else one CTA per 128 x bn tile.
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                                const CUtensorMap& out, int bn, int total_tiles, int n_tiles, cudaStream_t stream);
+                                bool pair, int bn, int total_units, int n_tiles, cudaStream_t stream);
 
 }  // namespace ur

@@ -26,18 +26,30 @@ constexpr int kMmaWarp = kNumAProd + kNumWProd;      // 5
 constexpr int kEpiWarp0 = kMmaWarp + 1;              // 6
 constexpr int kThreads = (kEpiWarp0 + 8) * 32;       // 448
 
-template <int BN>
-__host__ __device__ constexpr int pstages() {
-  return BN == 256 ? 4 : (BN == 160 ? 5 : (BN == 128 ? 6 : 8));
-}
+// PAIR = true: CTA pairs (cluster of 2) run tcgen05.mma.cta_group::2 on a 256 x BN tile; each CTA stages its own
+// 128 activation rows and HALF of the weight rows, which halves the weight traffic into shared memory (the main
+// loop of the single-CTA kernel is bound by shared-memory bandwidth: TMA write + UMMA read of A and W).
+template <int BN, bool PAIR>
+struct PCfg {
+  static constexpr int kWRows = PAIR ? BN / 2 : BN;
+  static constexpr int kWBytes = kWRows * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kWBytes;
+  static constexpr int kFixed = 2 * kEpiStageBytes + 4 * BN * 4 + 512;
+  static constexpr int kFit = (227 * 1024 - kFixed) / kStageBytes;
+  static constexpr int kStages = kFit > 8 ? 8 : kFit;
+  static constexpr int kSmem = kStages * kStageBytes + kFixed;
+};
 
 struct TileCoord {
   int n0, x0, y0, b0;
 };
-__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t, int n_tiles, int BN, int Wt, int Ht, int Bt) {
+// work unit u -> tile of this CTA: n tile = u % n_tiles (fastest), m tile = u / n_tiles (PAIR: 2 * that + cta rank)
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int n_tiles, int BN, int Wt, int Ht, int Bt,
+                                                int pair_rank) {
   TileCoord c;
-  const int nt = t % n_tiles;
-  int mt = t / n_tiles;
+  const int nt = u % n_tiles;
+  int mt = u / n_tiles;
+  if (pair_rank >= 0) mt = 2 * mt + pair_rank;
   c.n0 = nt * BN;
   const int tx = mt % p.tiles_x;
   mt /= p.tiles_x;
@@ -51,14 +63,14 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t, int 
 
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap mapA1,
                             const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW,
                             int total_tiles, int n_tiles) {
-  constexpr int STAGES = pstages<BN>();
-  constexpr int kWBytes = BN * kBlockK * 2;
-  constexpr int kStageBytes = kABytes + kWBytes;
+  using Cfg = PCfg<BN, PAIR>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int kStageBytes = Cfg::kStageBytes;
   constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + STAGES * kStageBytes;                          // [2 groups][128 x 80 B]
@@ -75,6 +87,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   const int Wt = 1 << p.wt_log2, Ht = 1 << p.ht_log2;
   const int Bt = kBlockM >> (p.wt_log2 + p.ht_log2);
   const int nkb = p.ntaps * p.cblocks;
+  // scheduling: work units (tiles, or 256-row pair tiles) are dealt round-robin to CTAs (or CTA pairs)
+  const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : -1;
+  const int u_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int u_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   if (tracing && threadIdx.x == 0) p.trace[7 * 16] = clock64();
 
@@ -88,16 +104,22 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 256);
+      mbar_init(&tempty_bar[s], PAIR ? 512 : 256);      // PAIR: the peer's epilogue threads arrive remotely on rank 0
     }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_2sm(tmem_slot, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();               // peer barriers initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tracing && threadIdx.x == 0) p.trace[7 * 16 + 1] = clock64();
@@ -106,8 +128,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     // =============================== activation TMA producers ===============================
     if (lane == 0) {
       int kiter = 0, it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt);
+      for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
+        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
         const int cbase = p.group_kc ? (tc.n0 / p.group_nc) * p.group_kc : 0;
         if (tracing && warp == 0 && it < 8) p.trace[0 * 16 + it] = clock64();
         int tap = 0, cb = 0;
@@ -116,16 +138,24 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
             const int s = kiter % STAGES;
             const uint32_t ph = (kiter / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_expect_tx(&full_bar[s], kStageBytes);     // covers the W bytes issued by the weight producer
+            // one arming arrive per stage (rank 0 only in PAIR mode), covering A and W bytes of both CTAs
+            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[s], PAIR ? 2 * kStageBytes : kStageBytes);
             const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
             const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
             const int c = cbase + cb * kBlockK;
             const int xi = tc.x0 * p.stride + dx, yi = tc.y0 * p.stride + dy;
             uint8_t* sa = smem + s * kStageBytes;
-            if (c < p.c1)
-              tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, tc.b0);
-            else
-              tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, tc.b0);
+            if constexpr (PAIR) {
+              if (c < p.c1)
+                tma_load_4d_2sm(sa, &mapA1, &full_bar[s], c, xi, yi, tc.b0);
+              else
+                tma_load_4d_2sm(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, tc.b0);
+            } else {
+              if (c < p.c1)
+                tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, tc.b0);
+              else
+                tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, tc.b0);
+            }
           }
           if (++cb == p.cblocks) {
             cb = 0;
@@ -139,16 +169,20 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     if (lane == 0) {
       const int me = warp - kNumAProd;
       int kiter = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt);
+      for (int t = u_first; t < total_tiles; t += u_stride) {
+        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
         const int wb = p.w_batched ? tc.b0 : 0;
+        const int wrow = PAIR ? tc.n0 + rank * (BN / 2) : tc.n0;     // PAIR: this CTA stages half of the N rows
         int tap = 0, cb = 0;
         for (int kb = 0; kb < nkb; ++kb, ++kiter) {
           if (kiter % kNumWProd == me) {
             const int s = kiter % STAGES;
             const uint32_t ph = (kiter / STAGES) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
-            tma_load_3d(smem + s * kStageBytes + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, tc.n0, wb);
+            if constexpr (PAIR)
+              tma_load_3d_2sm(smem + s * kStageBytes + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, wrow, wb);
+            else
+              tma_load_3d(smem + s * kStageBytes + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, wrow, wb);
           }
           if (++cb == p.cblocks) {
             cb = 0;
@@ -159,29 +193,39 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    if (lane == 0 && (!PAIR || rank == 0)) {
+      constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : kBlockM, BN);
       int kiter = 0, it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
         if (tracing && it < 8) p.trace[1 * 16 + it] = clock64();
+        // The full-barrier test of k-block kb+1 is issued BEFORE the MMAs of k-block kb: a try_wait costs ~200 cycles
+        // even when the phase is already complete, and the issuing thread is otherwise blocked on the MMA queue.
+        bool ready = mbar_test_wait(&full_bar[kiter % STAGES], (kiter / STAGES) & 1);
         for (int kb = 0; kb < nkb; ++kb, ++kiter) {
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (!ready) mbar_wait(&full_bar[s], ph);
           if (tracing && it < 8 && kb == 0) p.trace[2 * 16 + it] = clock64();
           tc_fence_after();
+          const int kn = kiter + 1;
+          ready = (kb + 1 < nkb) ? mbar_test_wait(&full_bar[kn % STAGES], (kn / STAGES) & 1) : false;
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint64_t da = umma_desc_k_sw128(sa);
           const uint64_t db = umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit(&empty_bar[s]);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if constexpr (PAIR)
+              tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (PAIR) tc_commit_2sm_mc(&empty_bar[s]); else tc_commit(&empty_bar[s]);
         }
-        tc_commit(&tfull_bar[as]);
+        if constexpr (PAIR) tc_commit_2sm_mc(&tfull_bar[as]); else tc_commit(&tfull_bar[as]);
         if (tracing && it < 8) p.trace[3 * 16 + it] = clock64();
       }
     }
@@ -205,21 +249,22 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     float a_nx = 0.f, m_nx = 1.f;                 // this thread's column of the NEXT tile's add / mul vectors
     auto fetch_vec = [&](int tt) {
-      const TileCoord tn = tile_coord(p, tt, n_tiles, BN, Wt, Ht, Bt);
+      const TileCoord tn = tile_coord(p, tt, n_tiles, BN, Wt, Ht, Bt, rank);
       const int n = tn.n0 + et;
       const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
+      const int bb = tn.b0 < p.B ? tn.b0 : p.B - 1;      // (a PAIR ghost tile lies past the last image)
       float a = 0.f;
       if (n < p.N) {
         if (p.bias) a += __ldg(p.bias + n);
-        if (p.rowvec) a += __ldg(p.rowvec + tn.b0 * p.rowvec_sb + n);
+        if (p.rowvec) a += __ldg(p.rowvec + bb * p.rowvec_sb + n);
       }
       a_nx = a;
-      m_nx = (has_mul && et < ncols && no0 + et < n_out) ? __ldg(p.chscale + tn.b0 * p.chscale_sb + no0 + et) : 1.f;
+      m_nx = (has_mul && et < ncols && no0 + et < n_out) ? __ldg(p.chscale + bb * p.chscale_sb + no0 + et) : 1.f;
     };
-    if (et < BN && static_cast<int>(blockIdx.x) < total_tiles) fetch_vec(blockIdx.x);
+    if (et < BN && u_first < total_tiles) fetch_vec(u_first);
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt);
+    for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
+      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
       const int nout0 = gated ? (tc.n0 >> 1) : tc.n0;
       const int as = it & 1;
       // ---- stage the per-column add / mul vectors of this tile (double-buffered by `as`); the values were
@@ -229,7 +274,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       if (et < BN) {
         add[et] = a_nx;
         mul[et] = m_nx;
-        const int tn = t + gridDim.x;
+        const int tn = t + u_stride;
         if (tn < total_tiles) fetch_vec(tn);
       }
       // global element offsets of the 4 rows this thread moves in the cooperative phases (-1: outside the tensor)
@@ -351,43 +396,66 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if constexpr (PAIR) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
       if (tracing && it < 8 && et == 0) p.trace[6 * 16 + it] = clock64();
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();               // the peer's shared memory / TMEM stay alive until both are done
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                    int total_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = pstages<BN>() * (kABytes + BN * kBlockK * 2) + 2 * kEpiStageBytes + 4 * BN * 4 + 512;
-  static_assert(smem <= 227 * 1024, "shared memory budget");
+                    int total_units, int n_tiles, cudaStream_t stream) {
+  using Cfg = PCfg<BN, PAIR>;
+  constexpr int smem = Cfg::kSmem;
+  static_assert(smem <= 227 * 1024 && Cfg::kStages >= 3, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, PAIR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm_persistent)");
     configured = true;
   }
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_gemm_persistent_kernel<BN><<<grid, kThreads, smem, stream>>>(p, a1, a2, w, total_tiles, n_tiles);
-  cudaError_t e = cudaGetLastError();
+  const int slots = PAIR ? num_sms() / 2 : num_sms();
+  const int units = total_units < slots ? total_units : slots;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? 2 * units : units);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_persistent_kernel<BN, PAIR>, p, a1, a2, w, total_units, n_tiles);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "conv_gemm_persistent launch");
 }
 
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                                const CUtensorMap& /*unused*/, int bn, int total_tiles, int n_tiles, cudaStream_t stream) {
+                                bool pair, int bn, int total_units, int n_tiles, cudaStream_t stream) {
+  if (pair) {
+    switch (bn) {
+      case 64: return launch_p<64, true>(p, a1, a2, w, total_units, n_tiles, stream);
+      case 128: return launch_p<128, true>(p, a1, a2, w, total_units, n_tiles, stream);
+      case 160: return launch_p<160, true>(p, a1, a2, w, total_units, n_tiles, stream);
+      default: return launch_p<256, true>(p, a1, a2, w, total_units, n_tiles, stream);
+    }
+  }
   switch (bn) {
-    case 64: return launch_p<64>(p, a1, a2, w, total_tiles, n_tiles, stream);
-    case 128: return launch_p<128>(p, a1, a2, w, total_tiles, n_tiles, stream);
-    case 160: return launch_p<160>(p, a1, a2, w, total_tiles, n_tiles, stream);
-    default: return launch_p<256>(p, a1, a2, w, total_tiles, n_tiles, stream);
+    case 64: return launch_p<64, false>(p, a1, a2, w, total_units, n_tiles, stream);
+    case 128: return launch_p<128, false>(p, a1, a2, w, total_units, n_tiles, stream);
+    case 160: return launch_p<160, false>(p, a1, a2, w, total_units, n_tiles, stream);
+    default: return launch_p<256, false>(p, a1, a2, w, total_units, n_tiles, stream);
   }
 }
 
