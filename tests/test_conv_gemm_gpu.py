@@ -164,3 +164,53 @@ def test_subpixel_phase_output_view():
     ref = bf16_round(F.linear(xb.float(), w.float()))
     assert_close(full[:, 1::2, 0::2], ref, TOL, "phase view")
     assert full[:, 0::2].abs().max().item() == 0.0
+
+
+@pytest.fixture
+def pair_mode():
+    """Force the persistent kernel's CTA-pair (tcgen05 cta_group::2) mode on / off; restores auto selection."""
+    from unirestore_b200 import _cabi
+
+    def setter(mode):
+        _cabi.ensure_init(0)
+        _cabi.lib().ur_debug_set_gemm_pair_mode(mode)
+    yield setter
+    _cabi.lib().ur_debug_set_gemm_pair_mode(-1)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("bn", [0, 64, 128, 160, 256])
+def test_conv3x3_pair_modes(pair_mode, mode, bn):
+    """Same conv through single-CTA and CTA-pair tiles, every N-tile width: odd k-block counts (45), an odd number of
+    M tiles (ghost pair tile), ragged N tiles, bias + residual epilogue."""
+    from unirestore_b200 import ops
+    pair_mode(mode)
+    for (B, H, W, Cin, Cout) in [(3, 16, 8, 320, 320), (1, 32, 32, 128, 640), (5, 8, 8, 64, 200)]:
+        x = _rand(B, Cin, H, W, seed=90)
+        w = _rand(Cout, Cin, 3, 3, seed=91, scale=(9 * Cin) ** -0.5)
+        b = _rand(Cout, seed=92)
+        r = _rand(B, H, W, Cout, seed=93).to(torch.bfloat16)
+        xb, wb = _nhwc(x), w.to(torch.bfloat16)
+        y = ops.conv_gemm(xb, ops.pack_conv_weight(wb), Cout, taps=ops.TAPS_3x3, bias=b, residual=r, bn=bn)
+        ref = bf16_round(F.conv2d(xb.float().permute(0, 3, 1, 2), wb.float(), b, padding=1).permute(0, 2, 3, 1)
+                         + r.float())
+        assert_close(y, ref, TOL, "conv3x3 pair=%d bn=%d %s" % (mode, bn, (B, H, W, Cin, Cout)))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_gated_and_linear_pair_modes(pair_mode, mode):
+    from unirestore_b200 import ops
+    pair_mode(mode)
+    M, K, N2 = 1000, 1280, 2560
+    x, w, b = _rand(M, K, seed=94), _rand(N2, K, seed=95, scale=K ** -0.5), _rand(N2, seed=96)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    bn = ops.pick_bn(N2, True)
+    wp, bp = ops.pack_gated_weight(wb, b, bn)
+    y = ops.conv_gemm(xb, wp, N2, bias=bp, act=ops.UR_ACT_GEGLU, bn=bn)
+    a, g = F.linear(xb.float(), wb.float(), b).chunk(2, -1)
+    assert_close(y, bf16_round(a * F.gelu(g)), TOL, "geglu pair=%d" % mode)
+    for (M, K, N) in [(300, 320, 320), (4096, 64, 960), (129, 1152, 72)]:
+        x, w, b = _rand(M, K, seed=97), _rand(N, K, seed=98, scale=K ** -0.5), _rand(N, seed=99)
+        xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+        y = ops.conv_gemm(xb, wb, N, bias=b)
+        assert_close(y, bf16_round(F.linear(xb.float(), wb.float(), b)), TOL, "linear pair=%d %s" % (mode, (M, K, N)))

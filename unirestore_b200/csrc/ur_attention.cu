@@ -57,7 +57,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
   int* xch = reinterpret_cast<int*>(tmem_slot + 2);       // [128] running row max (order-preserving int key) shared by the two half-row threads
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kTileQ;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -86,43 +86,47 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_T = tmem_base + 128;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // =============================== TMA producer (whole warp; the elected lane issues) ===============================
+    if (elect_one_sync()) {
       mbar_expect_tx(q_full, kQBytes);
 #pragma unroll
       for (int nb = 0; nb < ND; ++nb) tma_load_3d(sQ + nb * (kTileQ * 128), &mapQ, q_full, h * D + nb * 64, q0, b);
-      const int bk = p.kv_shared ? 0 : b;
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % kStages;
-        const uint32_t ph = (j / kStages) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
+    }
+    __syncwarp();
+    const int bk = p.kv_shared ? 0 : b;
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % kStages;
+      const uint32_t ph = (j / kStages) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      uint8_t* sk = sKV + s * 2 * kKBytes;
+      if (elect_one_sync()) {
         mbar_expect_tx(&kv_full[s], 2 * kKBytes);
-        uint8_t* sk = sKV + s * 2 * kKBytes;
 #pragma unroll
         for (int nb = 0; nb < ND; ++nb) {
           tma_load_3d(sk + nb * (kTileK * 128), &mapK, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
           tma_load_3d(sk + kKBytes + nb * (kTileK * 128), &mapV, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      mbar_wait(q_full, 0);
-      // S_j = Q K_j^T into TMEM columns [0,128); K_j lives in stage j % kStages
-      auto issue_s = [&](int j) {
-        const int s = j % kStages;
-        mbar_wait(&kv_full[s], (j / kStages) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sKV + s * 2 * kKBytes);
+    // =============================== MMA issuer (whole warp; the elected lane issues) ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
+    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
+    mbar_wait(q_full, 0);
+    // S_j = Q K_j^T into TMEM columns [0,128); K_j lives in stage j % kStages
+    auto issue_s = [&](int j) {
+      const int s = j % kStages;
+      mbar_wait(&kv_full[s], (j / kStages) & 1);
+      tc_fence_after();
+      const uint32_t aK = aKV + s * 2 * kKBytes;
+      if (elect_one_sync()) {
 #pragma unroll
         for (int nb = 0; nb < ND; ++nb) {
 #pragma unroll
@@ -132,24 +136,27 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
           }
         }
         tc_commit(s_full);
-      };
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j % kStages;
-        const uint32_t aV = smem_u32(sKV + s * 2 * kKBytes) + kKBytes;
-        const bool trm = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 4 && j < 8;
-        if (trm) p.trace[32 + (j - 4) * 8 + 0] = clock64();
-        // P_j is in shared memory and S_j has been consumed: S_{j+1} goes first so that the softmax warps can start
-        // on it while P_j V_j is still being issued / executed
-        mbar_wait(p_full, j & 1);
-        mbar_wait(s_empty, j & 1);
-        if (trm) p.trace[32 + (j - 4) * 8 + 1] = clock64();
-        if (j + 1 < nkv) issue_s(j + 1);
-        if (trm) p.trace[32 + (j - 4) * 8 + 2] = clock64();
-        // ---- T = P_j V_j
-        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
-        if (trm) p.trace[32 + (j - 4) * 8 + 3] = clock64();
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % kStages;
+      const uint32_t aV = aKV + s * 2 * kKBytes + kKBytes;
+      const bool trm = p.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 4 && j < 8;
+      if (trm) p.trace[32 + (j - 4) * 8 + 0] = clock64();
+      // P_j is in shared memory and S_j has been consumed: S_{j+1} goes first so that the softmax warps can start
+      // on it while P_j V_j is still being issued / executed
+      mbar_wait(p_full, j & 1);
+      mbar_wait(s_empty, j & 1);
+      if (trm) p.trace[32 + (j - 4) * 8 + 1] = clock64();
+      if (j + 1 < nkv) issue_s(j + 1);
+      if (trm) p.trace[32 + (j - 4) * 8 + 2] = clock64();
+      // ---- T = P_j V_j
+      if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+      if (trm) p.trace[32 + (j - 4) * 8 + 3] = clock64();
+      tc_fence_after();
+      if (elect_one_sync()) {
 #pragma unroll
         for (int nb = 0; nb < ND; ++nb) {
 #pragma unroll
@@ -163,8 +170,9 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
         }
         tc_commit(o_full);
         tc_commit(&kv_empty[s]);
-        if (trm) p.trace[32 + (j - 4) * 8 + 4] = clock64();
       }
+      __syncwarp();
+      if (trm) p.trace[32 + (j - 4) * 8 + 4] = clock64();
     }
   } else {
     // =============================== softmax / output: TWO threads per query row ===============================

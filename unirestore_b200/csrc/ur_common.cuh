@@ -15,6 +15,27 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ------------------------------------------------------------------ warp-uniform issue helpers
+// tcgen05.mma / TMA / commit take their operands from UNIFORM registers.  Inside an `if (lane == 0)` branch the
+// compiler cannot prove uniformity and wraps every such instruction in an ELECT + 5 x R2UR "waterfall" loop
+// (~100 cycles per instruction, measured: 650-700 cycles per 64-wide k-block in the MMA issuer).  The roles
+// therefore run their loops with the WHOLE warp (warp-uniform control flow and values) and predicate only the
+// issuing instructions with elect_one_sync().
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, known to the compiler as warp-uniform
+template <typename T>
+__device__ __forceinline__ T warp_uniform(T v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -176,7 +197,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_ma
 }
 
 // ------------------------------------------------------------------ math
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU ex2 + MUFU rcp (relative error ~1e-6, far below the bf16 rounding of the result)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -244,6 +266,60 @@ __device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(z)
       : "memory");
+}
+// Four back-to-back MMAs covering one 64-wide (128-byte swizzle atom) k-block: descriptors advance by 32 B (+2 in
+// the address field) per 16-element K step.  Taking the low / high descriptor words separately and stepping them
+// inside ONE asm block keeps the per-MMA issue cost at two uniform adds (no re-materialised 64-bit pairs).
+template <bool PAIR>
+__device__ __forceinline__ void tc_mma_bf16_x4(uint32_t tmem_d, uint32_t desc_hi, uint32_t a_lo, uint32_t b_lo,
+                                               uint32_t idesc, uint32_t accumulate) {
+  if constexpr (PAIR) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        ".reg .b32 z;\n"
+        "mov.b32 z, 0;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%2, %1};\n"
+        "mov.b64 db, {%3, %1};\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, {z, z, z, z, z, z, z, z}, p;\n"
+        "add.u64 da, da, 2;\n"
+        "add.u64 db, db, 2;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, {z, z, z, z, z, z, z, z}, p;\n"
+        "add.u64 da, da, 2;\n"
+        "add.u64 db, db, 2;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, {z, z, z, z, z, z, z, z}, p;\n"
+        "add.u64 da, da, 2;\n"
+        "add.u64 db, db, 2;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, {z, z, z, z, z, z, z, z}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(desc_hi), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "mov.b64 da, {%2, %1};\n"
+        "mov.b64 db, {%3, %1};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "add.u64 da, da, 2;\n"
+        "add.u64 db, db, 2;\n"
+        "setp.ne.b32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "add.u64 da, da, 2;\n"
+        "add.u64 db, db, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "add.u64 da, da, 2;\n"
+        "add.u64 db, db, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(desc_hi), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // Arrive (once all prior MMAs of this thread completed) on the mbarrier at the same offset in BOTH CTAs of the pair.
 __device__ __forceinline__ void tc_commit_2sm_mc(uint64_t* bar) {

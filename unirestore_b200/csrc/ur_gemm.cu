@@ -38,7 +38,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ C
   uint64_t* accum_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
 
   // ---- tile coordinates
@@ -71,47 +71,49 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      const int cbase = p.group_kc ? (n0 / p.group_nc) * p.group_kc : 0;
-      const int wb = p.w_batched ? b0 : 0;
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+    // =============================== TMA producer (whole warp; the elected lane issues) ===============================
+    const int cbase = p.group_kc ? (n0 / p.group_nc) * p.group_kc : 0;
+    const int wb = p.w_batched ? b0 : 0;
+    int tap = 0, cb = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&empty_bar[s], ph ^ 1);
+      uint8_t* sa = smem + s * kStageBytes;
+      const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
+      const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
+      const int c = cbase + cb * kBlockK;
+      const int xi = x0 * p.stride + dx, yi = y0 * p.stride + dy;
+      const bool src1 = c < p.c1;
+      const CUtensorMap* mp = src1 ? &mapA1 : &mapA2;
+      const int cc = src1 ? c : c - p.c1;
+      if (elect_one_sync()) {
         mbar_expect_tx(&full_bar[s], kStageBytes);
-        uint8_t* sa = smem + s * kStageBytes;
-        const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
-        const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
-        const int c = cbase + cb * kBlockK;
-        const int xi = x0 * p.stride + dx, yi = y0 * p.stride + dy;
-        if (c < p.c1)
-          tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, b0);
-        else
-          tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, b0);
+        tma_load_4d(sa, mp, &full_bar[s], cc, xi, yi, b0);
         tma_load_3d(sa + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, n0, wb);
-        if (++cb == p.cblocks) {
-          cb = 0;
-          ++tap;
-        }
+      }
+      __syncwarp();
+      if (++cb == p.cblocks) {
+        cb = 0;
+        ++tap;
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * kStageBytes);
-        const uint64_t da = umma_desc_k_sw128(sa);
-        const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+    // =============================== MMA issuer (whole warp; the elected lane issues) ===============================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BN);
+    const uint32_t smem_base = smem_u32(smem);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      const uint32_t sa = smem_base + s * kStageBytes;
+      const uint64_t da = umma_desc_k_sw128(sa);
+      const uint64_t db = umma_desc_k_sw128(sa + kABytes);
+      if (elect_one_sync()) {
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
           // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -119,8 +121,10 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ C
         }
         tc_commit(&empty_bar[s]);
       }
-      tc_commit(accum_bar);
+      __syncwarp();
     }
+    if (elect_one_sync()) tc_commit(accum_bar);
+    __syncwarp();
   } else {
     // =============================== epilogue ===============================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
@@ -300,7 +304,8 @@ extern "C" int ur_debug_set_gemm_pair_mode(int mode) {
   return old;
 }
 
-static void pick_tile_config(int n, long long m_tiles, int fixed_bn, bool pair_legal, int* bn_out, bool* pair_out) {
+static void pick_tile_config(int n, long long m_tiles, int nkb, int fixed_bn, bool pair_legal, int* bn_out,
+                             bool* pair_out) {
   const int cands[4] = {256, 160, 128, 64};
   const int sms = num_sms();
   double best_cost = -1.0;
@@ -313,10 +318,11 @@ static void pick_tile_config(int n, long long m_tiles, int fixed_bn, bool pair_l
     for (int pair = 0; pair < 2; ++pair) {
       if (pair && (!pair_legal || g_pair_mode == 0)) continue;
       if (!pair && pair_legal && g_pair_mode == 1) continue;
-      // Measured on B200 (tools/bench_gemm.py, round 1): pairs win only with full 256-wide N tiles and many waves
-      // (VAE 256/512-channel convs at 128^2..256^2: +9..16 %); they lose 3..15 % on the UNet's 2-4 wave problems
-      // and on 128/160-wide tiles, so auto mode keeps those on single CTAs.
-      if (pair && g_pair_mode < 0 && !(bn == 256 && n % 256 == 0 && m_tiles >= 8LL * sms)) continue;
+      // Measured on B200 (tools/exp_gemm_modes.py, round 1, after the warp-uniform issue path): CTA pairs win on every
+      // large-K problem with >= 160-wide N tiles (UNet 3x3 convs at 64^2..16^2: +9..16 %, VAE 256/512-channel convs:
+      // +10 %) because they halve the weight traffic L2 -> shared memory; they lose on small-K linears (epilogue
+      // bound, the cross-CTA accumulator hand-shake costs more than it saves) and with <= 128-wide tiles.
+      if (pair && g_pair_mode < 0 && !(bn >= 160 && nkb >= 18)) continue;
       double t, rounds;
       if (pair) {
         t = fmax(fmax(2.0 * bn, 256.0 + bn), 300.0);
@@ -371,7 +377,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
 
   int bn = 0;
   bool pair = false;
-  pick_tile_config(d->n, best_cost, d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : 0),
+  pick_tile_config(d->n, best_cost, d->ntaps * (((d->group_kc ? d->group_kc : ctot) + 63) / 64), d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : 0),
                    !d->w_batched && best_cost >= 2, &bn, &pair);
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
   if (gated && (d->n % bn)) return set_error(UR_ERR_ARG, "ur_conv_gemm: gated act needs n %% bn == 0");

@@ -82,7 +82,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
   const int Wt = 1 << p.wt_log2, Ht = 1 << p.ht_log2;
   const int Bt = kBlockM >> (p.wt_log2 + p.ht_log2);
@@ -121,112 +121,150 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();               // peer barriers initialised before any remote arrive / TMA
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
   if (tracing && threadIdx.x == 0) p.trace[7 * 16 + 1] = clock64();
 
   if (warp < kNumAProd) {
-    // =============================== activation TMA producers ===============================
-    if (lane == 0) {
-      int kiter = 0, it = 0;
-      for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
-        const int cbase = p.group_kc ? (tc.n0 / p.group_nc) * p.group_kc : 0;
-        if (tracing && warp == 0 && it < 8) p.trace[0 * 16 + it] = clock64();
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < nkb; ++kb, ++kiter) {
-          if (kiter % kNumAProd == warp) {
-            const int s = kiter % STAGES;
-            const uint32_t ph = (kiter / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
+    // =============================== activation TMA producers (whole warp, elected lane issues) ===============
+    int kiter = 0, it = 0;
+    for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
+      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
+      const int cbase = p.group_kc ? (tc.n0 / p.group_nc) * p.group_kc : 0;
+      if (tracing && lane == 0 && warp == 0 && it < 8) p.trace[0 * 16 + it] = clock64();
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++kiter) {
+        if (kiter % kNumAProd == warp) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          const bool trk = tracing && lane == 0 && warp == 0 && it == 1 && kb >= 6 && kb < 6 + 3 * 16;
+          if (trk) p.trace[192 + 4 * ((kb - 6) / 3)] = clock64();
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (trk) p.trace[192 + 4 * ((kb - 6) / 3) + 1] = clock64();
+          const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
+          const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
+          const int c = cbase + cb * kBlockK;
+          const int xi = tc.x0 * p.stride + dx, yi = tc.y0 * p.stride + dy;
+          uint8_t* sa = smem + s * kStageBytes;
+          const bool src1 = c < p.c1;
+          const CUtensorMap* mp = src1 ? &mapA1 : &mapA2;
+          const int cc = src1 ? c : c - p.c1;
+          if (elect_one_sync()) {
             // one arming arrive per stage (rank 0 only in PAIR mode), covering A and W bytes of both CTAs
             if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[s], PAIR ? 2 * kStageBytes : kStageBytes);
-            const int dy = static_cast<int>((p.dy_pack >> (4 * tap)) & 15) - 8;
-            const int dx = static_cast<int>((p.dx_pack >> (4 * tap)) & 15) - 8;
-            const int c = cbase + cb * kBlockK;
-            const int xi = tc.x0 * p.stride + dx, yi = tc.y0 * p.stride + dy;
-            uint8_t* sa = smem + s * kStageBytes;
-            if constexpr (PAIR) {
-              if (c < p.c1)
-                tma_load_4d_2sm(sa, &mapA1, &full_bar[s], c, xi, yi, tc.b0);
-              else
-                tma_load_4d_2sm(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, tc.b0);
-            } else {
-              if (c < p.c1)
-                tma_load_4d(sa, &mapA1, &full_bar[s], c, xi, yi, tc.b0);
-              else
-                tma_load_4d(sa, &mapA2, &full_bar[s], c - p.c1, xi, yi, tc.b0);
-            }
+            if constexpr (PAIR)
+              tma_load_4d_2sm(sa, mp, &full_bar[s], cc, xi, yi, tc.b0);
+            else
+              tma_load_4d(sa, mp, &full_bar[s], cc, xi, yi, tc.b0);
           }
-          if (++cb == p.cblocks) {
-            cb = 0;
-            ++tap;
-          }
+          __syncwarp();
+          if (trk) p.trace[192 + 4 * ((kb - 6) / 3) + 2] = clock64();
+        }
+        if (++cb == p.cblocks) {
+          cb = 0;
+          ++tap;
         }
       }
     }
   } else if (warp < kMmaWarp) {
     // =============================== weight TMA producers ===============================
-    if (lane == 0) {
-      const int me = warp - kNumAProd;
-      int kiter = 0;
-      for (int t = u_first; t < total_tiles; t += u_stride) {
-        const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
-        const int wb = p.w_batched ? tc.b0 : 0;
-        const int wrow = PAIR ? tc.n0 + rank * (BN / 2) : tc.n0;     // PAIR: this CTA stages half of the N rows
-        int tap = 0, cb = 0;
-        for (int kb = 0; kb < nkb; ++kb, ++kiter) {
-          if (kiter % kNumWProd == me) {
-            const int s = kiter % STAGES;
-            const uint32_t ph = (kiter / STAGES) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
+    const int me = warp - kNumAProd;
+    int kiter = 0, it = 0;
+    for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
+      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
+      const int wb = p.w_batched ? tc.b0 : 0;
+      const int wrow = PAIR ? tc.n0 + rank * (BN / 2) : tc.n0;     // PAIR: this CTA stages half of the N rows
+      int tap = 0, cb = 0;
+      for (int kb = 0; kb < nkb; ++kb, ++kiter) {
+        if (kiter % kNumWProd == me) {
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
+          const bool trk = tracing && lane == 0 && me == 0 && it == 1 && kb >= 6 && kb < 6 + 2 * 16;
+          if (trk) p.trace[256 + 4 * ((kb - 6) / 2)] = clock64();
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (trk) p.trace[256 + 4 * ((kb - 6) / 2) + 1] = clock64();
+          if (elect_one_sync()) {
             if constexpr (PAIR)
               tma_load_3d_2sm(smem + s * kStageBytes + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, wrow, wb);
             else
               tma_load_3d(smem + s * kStageBytes + kABytes, &mapW, &full_bar[s], tap * p.kc + cb * kBlockK, wrow, wb);
           }
-          if (++cb == p.cblocks) {
-            cb = 0;
-            ++tap;
-          }
+          __syncwarp();
+          if (trk) p.trace[256 + 4 * ((kb - 6) / 2) + 2] = clock64();
+        }
+        if (++cb == p.cblocks) {
+          cb = 0;
+          ++tap;
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer ===============================
-    if (lane == 0 && (!PAIR || rank == 0)) {
+    // whole warp, warp-uniform loop; only the tcgen05 instructions are predicated on the elected lane
+    if (!PAIR || rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : kBlockM, BN);
-      int kiter = 0, it = 0;
+      const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);   // descriptor low word of stage 0 (LBO = 1)
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SW128
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
       for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
-        if (tracing && it < 8) p.trace[1 * 16 + it] = clock64();
-        // The full-barrier test of k-block kb+1 is issued BEFORE the MMAs of k-block kb: a try_wait costs ~200 cycles
-        // even when the phase is already complete, and the issuing thread is otherwise blocked on the MMA queue.
-        bool ready = mbar_test_wait(&full_bar[kiter % STAGES], (kiter / STAGES) & 1);
-        for (int kb = 0; kb < nkb; ++kb, ++kiter) {
-          const int s = kiter % STAGES;
-          const uint32_t ph = (kiter / STAGES) & 1;
-          if (!ready) mbar_wait(&full_bar[s], ph);
-          if (tracing && it < 8 && kb == 0) p.trace[2 * 16 + it] = clock64();
-          tc_fence_after();
-          const int kn = kiter + 1;
-          ready = (kb + 1 < nkb) ? mbar_test_wait(&full_bar[kn % STAGES], (kn / STAGES) & 1) : false;
-          const uint32_t sa = smem_u32(smem + s * kStageBytes);
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sa + kABytes);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if constexpr (PAIR)
-              tc_mma_bf16_2sm(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else
-              tc_mma_bf16(tacc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        if (tracing && lane == 0 && it < 8) p.trace[1 * 16 + it] = clock64();
+        // Two k-blocks per iteration: the fixed cost of one trip through the issue path (barrier test, fence, elect,
+        // commit: ~250 cycles measured) is paid once per 8 MMAs.  The full-barrier tests of the NEXT two k-blocks are
+        // issued before the MMAs of the current ones so that their ~50-100 cycle latency is off the issue path.
+        bool ready0 = mbar_test_wait(&full_bar[stage], phase);
+        bool ready1 = false;
+        for (int kb = 0; kb < nkb; kb += 2) {
+          const bool two = kb + 1 < nkb;
+          const bool trk = tracing && lane == 0 && it == 1 && kb >= 8 && kb < 40;
+          if (trk) p.trace[128 + 4 * ((kb - 8) >> 1)] = clock64();
+          const uint32_t s0 = stage, ph0 = phase;
+          uint32_t s1 = s0 + 1, ph1 = ph0;
+          if (s1 == STAGES) {
+            s1 = 0;
+            ph1 ^= 1;
           }
-          if constexpr (PAIR) tc_commit_2sm_mc(&empty_bar[s]); else tc_commit(&empty_bar[s]);
+          if (!ready0) mbar_wait(&full_bar[s0], ph0);
+          if (two && !ready1) mbar_wait(&full_bar[s1], ph1);
+          if (trk) p.trace[128 + 4 * ((kb - 8) >> 1) + 1] = clock64();
+          if (tracing && lane == 0 && it < 8 && kb == 0) p.trace[2 * 16 + it] = clock64();
+          tc_fence_after();
+          // advance the ring past the k-blocks consumed here and pre-test the next two
+          stage = s1;
+          phase = ph1;
+          if (two && ++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          {
+            uint32_t n1 = stage + 1, nph1 = phase;
+            if (n1 == STAGES) {
+              n1 = 0;
+              nph1 ^= 1;
+            }
+            ready0 = (kb + 2 < nkb) ? mbar_test_wait(&full_bar[stage], phase) : false;
+            ready1 = (kb + 3 < nkb) ? mbar_test_wait(&full_bar[n1], nph1) : false;
+          }
+          const uint32_t alo0 = a_lo0 + s0 * (kStageBytes >> 4);           // (smem address >> 4) of the A tiles
+          const uint32_t alo1 = a_lo0 + s1 * (kStageBytes >> 4);
+          if (elect_one_sync()) {
+            tc_mma_bf16_x4<PAIR>(tacc, kDescHi, alo0, alo0 + (kABytes >> 4), idesc, kb != 0 ? 1u : 0u);
+            if constexpr (PAIR) tc_commit_2sm_mc(&empty_bar[s0]); else tc_commit(&empty_bar[s0]);
+            if (two) {
+              tc_mma_bf16_x4<PAIR>(tacc, kDescHi, alo1, alo1 + (kABytes >> 4), idesc, 1u);
+              if constexpr (PAIR) tc_commit_2sm_mc(&empty_bar[s1]); else tc_commit(&empty_bar[s1]);
+            }
+          }
+          if (trk) p.trace[128 + 4 * ((kb - 8) >> 1) + 2] = clock64();
         }
-        if constexpr (PAIR) tc_commit_2sm_mc(&tfull_bar[as]); else tc_commit(&tfull_bar[as]);
-        if (tracing && it < 8) p.trace[3 * 16 + it] = clock64();
+        if (elect_one_sync()) {
+          if constexpr (PAIR) tc_commit_2sm_mc(&tfull_bar[as]); else tc_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (tracing && lane == 0 && it < 8) p.trace[3 * 16 + it] = clock64();
       }
     }
   } else {
@@ -307,10 +345,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
       for (; c < ncols; c += 64) {
+        const bool tre = tracing && it == 1 && et == 0 && c < 192;
+        if (tre) p.trace[320 + (c >> 6) * 8] = clock64();
         uint32_t va[32];
         tmem_ld32(trow + c, va);
         // (A) staging tile is free again; park the prefetched residual chunk in it
         group_barrier(2 + grp);
+        if (tre) p.trace[320 + (c >> 6) * 8 + 1] = clock64();
         if (p.residual) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -328,6 +369,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         float f[32];
         if (plain) {
           tmem_ld_wait();
+          if (tre) p.trace[320 + (c >> 6) * 8 + 2] = clock64();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 ad = *reinterpret_cast<const float4*>(add + c + 4 * j);
@@ -372,7 +414,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           *sp = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                            pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
         }
+        if (tre) p.trace[320 + (c >> 6) * 8 + 3] = clock64();
         group_barrier(6 + grp);
+        if (tre) p.trace[320 + (c >> 6) * 8 + 4] = clock64();
         // (C) coalesced write-out: a warp stores 8 rows x 64 contiguous bytes per instruction
         {
           const int col = c + cchunk * 8;
@@ -394,6 +438,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
             }
           }
         }
+        if (tre) p.trace[320 + (c >> 6) * 8 + 5] = clock64();
       }
       tc_fence_before();
       if constexpr (PAIR) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);

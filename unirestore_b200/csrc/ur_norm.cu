@@ -24,17 +24,24 @@ __global__ void chan_stats_kernel(const bf16* __restrict__ x, long long ld, long
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const bf16* base = x + b * img_stride + cv * 8;
-  for (int p = p0 + pl; p < p1; p += PL) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + p * ld));
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  for (int p = p0 + pl; p < p1; p += 4 * PL) {
+    uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a, c;
-      unpack_bf16(u[j], a, c);
-      s[2 * j] += a;
-      q[2 * j] += a * a;
-      s[2 * j + 1] += c;
-      q[2 * j + 1] += c * c;
+    for (int i = 0; i < 4; ++i)
+      v[i] = (p + i * PL < p1) ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(p + i * PL) * ld))
+                               : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a, c;
+        unpack_bf16(u[j], a, c);
+        s[2 * j] += a;
+        q[2 * j] += a * a;
+        s[2 * j + 1] += c;
+        q[2 * j + 1] += c * c;
+      }
     }
   }
 #pragma unroll
@@ -92,23 +99,31 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
   bf16* dst = out + b * iso + c0;
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(P, p0 + chunk);
-  for (int p = p0 + pl; p < p1; p += PL) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + p * lds));
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
+  // four independent 16-byte loads in flight per thread (the kernel is latency-bound otherwise)
+  for (int p = p0 + pl; p < p1; p += 4 * PL) {
+    uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a, c;
-      unpack_bf16(u[j], a, c);
-      a = a * sc[2 * j] + sf[2 * j];
-      c = c * sc[2 * j + 1] + sf[2 * j + 1];
-      if (silu) {
-        a = silu_f(a);
-        c = silu_f(c);
+    for (int i = 0; i < 4; ++i)
+      if (p + i * PL < p1) v[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p + i * PL) * lds));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (p + i * PL >= p1) break;
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a, c;
+        unpack_bf16(u[j], a, c);
+        a = a * sc[2 * j] + sf[2 * j];
+        c = c * sc[2 * j + 1] + sf[2 * j + 1];
+        if (silu) {
+          a = silu_f(a);
+          c = silu_f(c);
+        }
+        o[j] = pack_bf16(a, c);
       }
-      o[j] = pack_bf16(a, c);
+      *reinterpret_cast<uint4*>(dst + static_cast<long long>(p + i * PL) * ldo) = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<uint4*>(dst + p * ldo) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
