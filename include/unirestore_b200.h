@@ -114,6 +114,15 @@ int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int batch, int 
 int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2, int64_t is2, int c2,
                   const double* stats, int groups, int batch, int pixels, const float* gamma, const float* beta,
                   float eps, int silu, void* out, int64_t ldo, int64_t iso, void* stream);
+/* One-launch nn.GroupNorm (+SiLU) over cat(x1, x2): a thread-block cluster per image keeps the partial statistics in
+ * distributed shared memory, so there is no statistics array and no second launch (ur_groupnorm_cluster.cu).  Same
+ * reference call sites as ur_norm_apply; meant for tensors that stay L2-resident between its two passes. */
+int ur_group_norm(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2, int64_t is2, int c2,
+                  int groups, int batch, int pixels, const float* gamma, const float* beta, float eps, int silu,
+                  void* out, int64_t ldo, int64_t iso, void* stream);
+/* cluster size ur_group_norm launches with on this device (16 when the non-portable size is available, else 8). */
+int ur_group_norm_cluster_size(void);
+int ur_debug_set_group_norm_cluster(int n);   /* development: override the cluster size (0 = probe) */
 /* nn.LayerNorm over the channel dim of every token (BasicTransformerBlock.norm1-3; timm LayerNorm2d nafnet_arch.py:97-98). */
 int ur_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t rows, int channels, const float* gamma,
                  const float* beta, float eps, void* stream);

@@ -9,7 +9,7 @@ import os
 import pytest
 import torch
 
-from tests.util import assert_close
+from tests.util import assert_close, bf16_round
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -166,3 +166,29 @@ def test_controller_golden():
     assert set(y) == set(g["out"])
     for k in y:
         assert_close(y[k], g["out"][k].to(DEV), 3e-2, "Controller[%d] vs reference golden" % k)
+
+
+@pytest.mark.parametrize("B,H,W,C1,C2,G,silu", [(2, 16, 16, 320, 0, 32, True), (3, 8, 8, 1280, 1280, 32, True),
+                                                 (1, 64, 64, 640, 320, 32, False), (8, 4, 4, 256, 0, 32, True),
+                                                 (2, 5, 7, 64, 32, 8, False), (1, 3, 3, 64, 0, 32, True)])
+def test_group_norm_cluster_kernel(B, H, W, C1, C2, G, silu):
+    """ur_group_norm (cluster / DSMEM kernel) against torch GroupNorm on the same bf16 inputs, incl. the two-source
+    concat, slabs that do not divide the pixel count, fewer pixels than CTAs, and against the two-launch path."""
+    import torch.nn.functional as F
+    from unirestore_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    x1 = (torch.randn(B, H, W, C1, generator=g) * 2 + 0.5).to(dev).to(torch.bfloat16)
+    x2 = (torch.randn(B, H, W, C2, generator=g) - 0.3).to(dev).to(torch.bfloat16) if C2 else None
+    gamma = torch.randn(C1 + C2, generator=g).to(dev)
+    beta = torch.randn(C1 + C2, generator=g).to(dev)
+    y = ops.group_norm(x1, G, gamma, beta, 1e-5, silu=silu, x2=x2)
+    xc = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), G, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+    assert_close(y, bf16_round(ref), 2e-3, "cluster group_norm")
+    st = ops.chan_stats(x1, total_channels=C1 + C2)
+    if C2:
+        ops.chan_stats(x2, stats=st, offset=C1, total_channels=C1 + C2, zero=False)
+    y2 = ops.norm_apply(x1, st, G, gamma, beta, 1e-5, silu, x2)
+    assert_close(y, y2, 5e-3, "cluster vs two-launch group_norm")

@@ -2,7 +2,7 @@
 TAG=${1:-cX}
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-( time timeout 1200 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest.log 2>&1
+( time timeout 600 python -m pytest tests -m gpu -x -q --timeout 120 ) > gpurun_out/${TAG}_pytest.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log
 timeout 300 python tools/trace_gemm.py unet_c3_320_64:160:0 unet_c3_320_64:160:1 vae_c3_128_512:128:0 unet_c3_320_64:64:0 lin_320_320_4096:160:0 > gpurun_out/${TAG}_trace.log 2>&1
 timeout 300 python tools/bench_gemm.py > gpurun_out/${TAG}_bench_gemm.log 2>&1

@@ -54,6 +54,9 @@ SIGNATURES = {
     "ur_debug_set_gemm_pair_mode": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_trace": (C.c_int, [_P]),
     "ur_chan_stats": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _I, _I, _P]),
+    "ur_group_norm": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _I, _I, _I, _P, _P, _F, _I, _P, _I64, _I64, _P]),
+    "ur_group_norm_cluster_size": (C.c_int, []),
+    "ur_debug_set_group_norm_cluster": (C.c_int, [C.c_int]),
     "ur_norm_apply": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _I64,
                                 _I64, _P]),
     "ur_layernorm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P]),

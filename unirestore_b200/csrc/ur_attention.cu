@@ -6,9 +6,12 @@
 //   warp 0      TMA producer: Q once, then a 2-stage ring of (K_j, V_j) tiles (128-byte swizzled boxes)
 //   warp 1      single-thread tcgen05.mma issuer:  S = Q K_j^T   (128x128 fp32 in TMEM columns [0,128))
 //                                                   T = P_j V_j   (128xD   fp32 in TMEM columns [128,128+D))
-//   warps 2..5  softmax: ONE THREAD PER QUERY ROW (TMEM lane) -> row max / sum need no shuffles.  Two TMEM passes
-//               over S (max, then exp2 + bf16 pack), P_j written to shared memory in the K-major SW128 UMMA
-//               layout, running O kept in registers and rescaled by exp2(m_old - m_new) per tile.
+//   warps 2..9  softmax: TWO THREADS PER QUERY ROW (TMEM lane; 64 score columns each) -> no shuffles.  Two TMEM
+//               passes over S (max, then exp2 + bf16 pack), P_j written to shared memory in the K-major SW128 UMMA
+//               layout.  O ACCUMULATES IN TMEM across KV tiles (P V issued with accumulate); the softmax reference
+//               maximum is only moved - and O / l rescaled in TMEM by exp2(m_ref - m_new) - when the running row
+//               maximum has grown by more than 2^8 since the reference was set (lazy rescaling: P <= 256 stays
+//               exact in bf16 / fp32; softmax is shift-invariant, so the result is unchanged).
 // P V^T uses V exactly as TMA lands it ([keys, D] rows of 128 B) through an MN-major UMMA descriptor.
 // With D = 64 a CTA needs 112 KB smem and 256 TMEM columns, so two CTAs share an SM and one CTA's softmax
 // overlaps the other's MMAs.
@@ -76,7 +79,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
     mbar_init(s_empty, 256);
     mbar_init(p_full, 256);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 256);
+    mbar_init(o_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -152,8 +155,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       if (trm) p.trace[32 + (j - 4) * 8 + 1] = clock64();
       if (j + 1 < nkv) issue_s(j + 1);
       if (trm) p.trace[32 + (j - 4) * 8 + 2] = clock64();
-      // ---- T = P_j V_j
-      if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+      // ---- O += P_j V_j (any rescaling of O for tile j happened before the p_full arrivals)
       if (trm) p.trace[32 + (j - 4) * 8 + 3] = clock64();
       tc_fence_after();
       if (elect_one_sync()) {
@@ -165,7 +167,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
             const uint64_t da = umma_desc_k_sw128(aP + (k >> 2) * (kTileQ * 128)) + 2 * (k & 3);
             // B = V: MN-major, 16 keys = 16 rows of 128 B
             const uint64_t db = umma_desc_mn_sw128(aV + nb * (kTileK * 128) + k * 16 * 128, kTileK * 128);
-            tc_mma_bf16(tmem_T + nb * 64, da, db, idesc_pv, k != 0 ? 1u : 0u);
+            tc_mma_bf16(tmem_T + nb * 64, da, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
           }
         }
         tc_commit(o_full);
@@ -186,10 +188,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t tS = tmem_S + lane_off + hf * 64;
     const uint32_t tT = tmem_T + lane_off + hf * DH;
-    float O[DH];
-#pragma unroll
-    for (int i = 0; i < DH; ++i) O[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;             // m: reference maximum (log2 domain) the exponentials are taken against
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     uint8_t* prow = sP + hf * (kTileQ * 128) + r * 128;        // key block hf (64 keys) of the P tile, row r
     int* my_x = xch + r;
@@ -225,29 +224,35 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       }
       atomicMax(my_x, f2key(raw));
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float mx = key2f(*my_x) * p.scale_log2;    // running max over all tiles so far, log2 domain (>= m)
-      const float alpha = exp2_approx(m - mx);         // m = -inf on the first tile -> 0
+      const float mx = key2f(*my_x) * p.scale_log2;    // running max over all tiles so far, log2 domain
+      // ---- lazy rescaling: move the reference only when the running max outgrew it by more than 2^8 (always on
+      //      the first tile).  tcgen05.ld/st are warp-collective, so the warp goes through the O update when ANY of
+      //      its rows needs it; rows that do not get alpha = 1.  Both threads of a row see the same history of
+      //      *my_x, hence take identical decisions.
+      const bool need = (j == 0) || (mx - m > 8.0f);
       if (trs) p.trace[(j - 4) * 8 + 2] = clock64();
-      // ---- fold the previous tile's P V into the running output (O = (O + T) * alpha)
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
-        if (trs) p.trace[(j - 4) * 8 + 3] = clock64();
-        tc_fence_after();
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? exp2_approx(m - mx) : 1.0f;       // j == 0: exp2(-inf) = 0, but O is not read then
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);                             // P_{j-1} V_{j-1} has landed in TMEM
+          tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < DH / 32; ++c) {
-          uint32_t t0[32];
-          tmem_ld32(tT + c * 32, t0);
-          tmem_ld_wait();
+          for (int c = 0; c < DH / 32; ++c) {
+            uint32_t t0[32];
+            tmem_ld32(tT + c * 32, t0);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) O[c * 32 + i] = (O[c * 32 + i] + __uint_as_float(t0[i])) * alpha;
+            for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * alpha);
+            tmem_st32(tT + c * 32, t0);
+          }
+          tmem_st_wait();
+          l *= alpha;
         }
-        tc_fence_before();
-        mbar_arrive(o_empty);
+        if (need) m = mx;
       }
-      l *= alpha;
       if (trs) p.trace[(j - 4) * 8 + 4] = clock64();
       // ---- pass 2: P = exp2(s * scale - max) -> bf16 -> shared memory (K-major SW128), partial row sum
-      const float nmx = -mx;
+      const float nmx = -m;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -289,18 +294,18 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       fence_proxy_async_smem();
       mbar_arrive(p_full);
       if (trs) p.trace[(j - 4) * 8 + 6] = clock64();
-      m = mx;
     }
     // ---- last tile's P V, combine the two partial row sums, normalise, store
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
+    float O[DH];
 #pragma unroll
     for (int c = 0; c < DH / 32; ++c) {
       uint32_t t0[32];
       tmem_ld32(tT + c * 32, t0);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(t0[i]);
+      for (int i = 0; i < 32; ++i) O[c * 32 + i] = __uint_as_float(t0[i]);
     }
     // combine the two partial row sums through the same slot (two rounds: hf 0 publishes, hf 1 adds and publishes)
     asm volatile("bar.sync 1, 256;" ::: "memory");

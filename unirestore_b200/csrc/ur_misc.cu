@@ -75,49 +75,61 @@ __global__ void transpose_tokens_kernel(const bf16* __restrict__ x, long long ld
 __global__ void dwconv3x3_gate_kernel(const bf16* __restrict__ x, int H, int W, int c, const float* __restrict__ wgt,
                                       const float* __restrict__ bias, bf16* __restrict__ y, double* __restrict__ stats,
                                       int CV, int PL, int chunk) {
-  extern __shared__ float sh[];  // pooled[c]
+  extern __shared__ __align__(16) float sh[];  // pooled[c] | weights transposed to [9][2c] (tap-major, 128-bit reads)
+  const int C2 = 2 * c;
+  float* s_pool = sh;
+  float* s_w = sh + c;
   const int b = blockIdx.y;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) s_pool[i] = 0.f;
+  for (int i = threadIdx.x; i < 9 * C2; i += blockDim.x) s_w[(i % 9) * C2 + i / 9] = __ldg(wgt + i);
   __syncthreads();
-  const int C2 = 2 * c;
   const int P = H * W;
   const int p0 = blockIdx.x * chunk, p1 = min(P, p0 + chunk);
   const bf16* xb = x + static_cast<long long>(b) * P * C2;
-  float pool[8];
+  float pool[8], ba[8], bg[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) pool[j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    pool[j] = 0.f;
+    ba[j] = __ldg(bias + cv * 8 + j);
+    bg[j] = __ldg(bias + c + cv * 8 + j);
+  }
   for (int p = p0 + pl; p < p1; p += PL) {
     const int py = p / W, px = p % W;
     float a[8], g[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      a[j] = __ldg(bias + cv * 8 + j);
-      g[j] = __ldg(bias + c + cv * 8 + j);
+      a[j] = ba[j];
+      g[j] = bg[j];
+    }
+    // issue the (up to) 18 activation loads of the 3x3 window first, then the FMAs
+    uint4 va[9], vg[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const bf16* src = xb + (static_cast<long long>(ok ? yy : py) * W + (ok ? xx : px)) * C2 + cv * 8;
+      va[t] = ok ? __ldg(reinterpret_cast<const uint4*>(src)) : make_uint4(0u, 0u, 0u, 0u);
+      vg[t] = ok ? __ldg(reinterpret_cast<const uint4*>(src + c)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int yy = py + ky - 1;
-      if (yy < 0 || yy >= H) continue;
+    for (int t = 0; t < 9; ++t) {
+      const float4 wa0 = *reinterpret_cast<const float4*>(s_w + t * C2 + cv * 8);
+      const float4 wa1 = *reinterpret_cast<const float4*>(s_w + t * C2 + cv * 8 + 4);
+      const float4 wg0 = *reinterpret_cast<const float4*>(s_w + t * C2 + c + cv * 8);
+      const float4 wg1 = *reinterpret_cast<const float4*>(s_w + t * C2 + c + cv * 8 + 4);
+      const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
+      const float wg[8] = {wg0.x, wg0.y, wg0.z, wg0.w, wg1.x, wg1.y, wg1.z, wg1.w};
+      const uint32_t ua[4] = {va[t].x, va[t].y, va[t].z, va[t].w}, ug[4] = {vg[t].x, vg[t].y, vg[t].z, vg[t].w};
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int xx = px + kx - 1;
-        if (xx < 0 || xx >= W) continue;
-        const bf16* src = xb + (static_cast<long long>(yy) * W + xx) * C2 + cv * 8;
-        const uint4 va = __ldg(reinterpret_cast<const uint4*>(src));
-        const uint4 vg = __ldg(reinterpret_cast<const uint4*>(src + c));
-        const uint32_t ua[4] = {va.x, va.y, va.z, va.w}, ug[4] = {vg.x, vg.y, vg.z, vg.w};
-        const int t = ky * 3 + kx;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float f0, f1;
-          unpack_bf16(ua[j], f0, f1);
-          a[2 * j] += f0 * __ldg(wgt + (cv * 8 + 2 * j) * 9 + t);
-          a[2 * j + 1] += f1 * __ldg(wgt + (cv * 8 + 2 * j + 1) * 9 + t);
-          unpack_bf16(ug[j], f0, f1);
-          g[2 * j] += f0 * __ldg(wgt + (c + cv * 8 + 2 * j) * 9 + t);
-          g[2 * j + 1] += f1 * __ldg(wgt + (c + cv * 8 + 2 * j + 1) * 9 + t);
-        }
+      for (int j = 0; j < 4; ++j) {
+        float f0, f1;
+        unpack_bf16(ua[j], f0, f1);
+        a[2 * j] += f0 * wa[2 * j];
+        a[2 * j + 1] += f1 * wa[2 * j + 1];
+        unpack_bf16(ug[j], f0, f1);
+        g[2 * j] += f0 * wg[2 * j];
+        g[2 * j + 1] += f1 * wg[2 * j + 1];
       }
     }
     uint32_t o[4];
@@ -134,10 +146,10 @@ __global__ void dwconv3x3_gate_kernel(const bf16* __restrict__ x, int H, int W, 
     *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * P + p) * c + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&sh[cv * 8 + j], pool[j]);
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_pool[cv * 8 + j], pool[j]);
   __syncthreads();
   for (int i = threadIdx.x; i < c; i += blockDim.x)
-    atomicAdd(stats + (static_cast<long long>(b) * c + i) * 2, static_cast<double>(sh[i]));
+    atomicAdd(stats + (static_cast<long long>(b) * c + i) * 2, static_cast<double>(s_pool[i]));
 }
 
 // ------------------------------------------------------------------------------------ small_linear
@@ -417,18 +429,18 @@ extern "C" int ur_transpose_tokens(const void* x, int64_t ld, int64_t batch_stri
 extern "C" int ur_dwconv3x3_gate(const void* x, int batch, int h, int w, int c, const float* weight, const float* bias,
                                  void* y, double* stats, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!x || !weight || !bias || !y || !stats || c % 8 || c > 4096)
+  if (!x || !weight || !bias || !y || !stats || c % 8 || 19 * static_cast<size_t>(c) * sizeof(float) > 48 * 1024)
     return set_error(UR_ERR_ARG, "ur_dwconv3x3_gate: bad arguments");
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * static_cast<size_t>(batch) * c, stream);
   if (e != cudaSuccess) return set_cuda_error(e, "ur_dwconv3x3_gate memset");
   const int CV = c / 8;
   const int PL = CV >= 256 ? 1 : 256 / CV;
   const int P = h * w;
-  const int target = max(1, (8 * num_sms()) / batch);
+  const int target = max(1, (4 * num_sms()) / batch);
   int chunk = (P + target - 1) / target;
   if (chunk < PL * 2) chunk = PL * 2;
   dim3 grid((P + chunk - 1) / chunk, batch);
-  dwconv3x3_gate_kernel<<<grid, CV * PL, c * sizeof(float), stream>>>(static_cast<const bf16*>(x), h, w, c, weight, bias,
+  dwconv3x3_gate_kernel<<<grid, CV * PL, (c + 18 * static_cast<size_t>(c)) * sizeof(float), stream>>>(static_cast<const bf16*>(x), h, w, c, weight, bias,
                                                                      static_cast<bf16*>(y), stats, CV, PL, chunk);
   UR_LAUNCH_CHECK("ur_dwconv3x3_gate");
 }

@@ -128,60 +128,88 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
 }
 
 // ------------------------------------------------------------------------------------ layernorm
-// One warp per token; the row lives in registers (C <= 8*32*NV), exact two-pass mean / variance.
-template <int NV>
+// One warp per R consecutive tokens; the rows live in registers (C <= 8*32*NV), exact two-pass mean / variance.
+// All R * NV 16-byte loads of a warp are issued before the first reduction (the kernel is latency-bound otherwise).
+template <int NV, int R>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
                                  int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= M) return;
   const int nvec = C >> 3;
-  float v[NV][8];
-  float sum = 0.f;
+  float v[R][NV][8];
+  float sum[R], sq[R];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
-    if (vi < nvec) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vi * 8));
+  for (int r = 0; r < R; ++r) {
+    const bool row_ok = row0 + r < M;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && vi < nvec) t = __ldg(reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + vi * 8));
       const uint32_t u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        unpack_bf16(u[j], v[i][2 * j], v[i][2 * j + 1]);
-        sum += v[i][2 * j] + v[i][2 * j + 1];
+      for (int j = 0; j < 4; ++j) unpack_bf16(u[j], v[r][i][2 * j], v[r][i][2 * j + 1]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    sum[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum[r] += v[r][i][j];          // padded vectors are zero
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < R; ++r) sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], o);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float mean = sum[r] / C;
+    sum[r] = mean;
+    sq[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[r][i][j] - mean;
+          sq[r] += d * d;
+        }
       }
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float sq = 0.f;
+  for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (lane + 32 * i < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mean;
-        sq += d * d;
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / C + eps);
+    for (int r = 0; r < R; ++r) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
     if (vi < nvec) {
-      uint32_t o[4];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+      const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = vi * 8 + 2 * j;
-        const float a = (v[i][2 * j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        const float d = (v[i][2 * j + 1] - mean) * rstd * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-        o[j] = pack_bf16(a, d);
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r < M) {
+          const float mean = sum[r];
+          const float rstd = rsqrtf(sq[r] / C + eps);
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = (v[r][i][2 * j] - mean) * rstd * ga[2 * j] + be[2 * j];
+            const float d = (v[r][i][2 * j + 1] - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1];
+            o[j] = pack_bf16(a, d);
+          }
+          *reinterpret_cast<uint4*>(out + (row0 + r) * ldo + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
-      *reinterpret_cast<uint4*>(out + row * ldo + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
 }
@@ -268,19 +296,21 @@ extern "C" int ur_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo, 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!x || !out || !gamma || !beta || channels % 8 || channels > 2048 || ldx % 8 || ldo % 8 || rows <= 0)
     return set_error(UR_ERR_ARG, "ur_layernorm: bad arguments (C=%d)", channels);
-  const int warps = 8;
-  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+  if ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15)
+    return set_error(UR_ERR_ARG, "ur_layernorm: gamma / beta must be 16-byte aligned");
+  const int warps = 4;
   const bf16* xp = static_cast<const bf16*>(x);
   bf16* op = static_cast<bf16*>(out);
   const int M = static_cast<int>(rows);
+  auto blocks = [&](int r) { return static_cast<unsigned>((rows + static_cast<int64_t>(warps) * r - 1) / (warps * r)); };
   if (channels <= 256)
-    layernorm_kernel<1><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    layernorm_kernel<1, 4><<<blocks(4), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   else if (channels <= 512)
-    layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    layernorm_kernel<2, 4><<<blocks(4), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   else if (channels <= 1280)
-    layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    layernorm_kernel<5, 2><<<blocks(2), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   else
-    layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    layernorm_kernel<8, 1><<<blocks(1), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_layernorm launch");
 }

@@ -199,10 +199,28 @@ def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None
     return out
 
 
+FUSED_GN_MAX_BYTES = 96 << 20      # above this the tensor does not survive in L2 between the two passes
+
+
 def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
-    """nn.GroupNorm (+SiLU) over ``cat(x, x2)``: two launches (statistics, apply)."""
-    C1 = x.shape[-1]
+    """nn.GroupNorm (+SiLU) over ``cat(x, x2)``.
+
+    L2-resident tensors (every per-step GroupNorm): ONE launch of the cluster kernel ``ur_group_norm`` (statistics
+    in distributed shared memory).  Larger tensors (VAE levels): ``ur_chan_stats`` (per source) + ``ur_norm_apply``."""
+    B, P, C1, ld1, is1 = _geom(x)
     C2 = x2.shape[-1] if x2 is not None else 0
+    if B * P * (C1 + C2) * 2 <= FUSED_GN_MAX_BYTES and (C1 + C2) <= 8192:
+        ld2, is2 = 0, 0
+        if x2 is not None:
+            B2, P2, C2, ld2, is2 = _geom(x2)
+            if (B2, P2) != (B, P):
+                raise ValueError("x2 shape mismatch")
+        out = torch.empty(tuple(x.shape[:-1]) + (C1 + C2,), device=x.device, dtype=torch.bfloat16)
+        _, _, _, ldo, iso = _geom(out)
+        check(_lib().ur_group_norm(_ptr(x), ld1, is1, C1, _ptr(x2), ld2, is2, C2, groups, B, P, _f32(gamma, "gamma"),
+                                   _f32(beta, "beta"), eps, int(silu), _ptr(out), ldo, iso, _stream()),
+              "ur_group_norm")
+        return out
     stats = chan_stats(x, total_channels=C1 + C2)
     if x2 is not None:
         chan_stats(x2, stats=stats, offset=C1, total_channels=C1 + C2, zero=False)
