@@ -182,7 +182,12 @@ def test_group_norm_cluster_kernel(B, H, W, C1, C2, G, silu):
     x2 = (torch.randn(B, H, W, C2, generator=g) - 0.3).to(dev).to(torch.bfloat16) if C2 else None
     gamma = torch.randn(C1 + C2, generator=g).to(dev)
     beta = torch.randn(C1 + C2, generator=g).to(dev)
-    y = ops.group_norm(x1, G, gamma, beta, 1e-5, silu=silu, x2=x2)
+    old = ops.FUSED_GN_MAX_BYTES
+    ops.FUSED_GN_MAX_BYTES = 1 << 40            # route through the cluster kernel
+    try:
+        y = ops.group_norm(x1, G, gamma, beta, 1e-5, silu=silu, x2=x2)
+    finally:
+        ops.FUSED_GN_MAX_BYTES = old
     xc = torch.cat([x1, x2], -1) if C2 else x1
     ref = F.group_norm(xc.float().permute(0, 3, 1, 2), G, gamma, beta, 1e-5)
     ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)

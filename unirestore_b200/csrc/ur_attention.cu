@@ -148,13 +148,13 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       const uint32_t aV = aKV + s * 2 * kKBytes + kKBytes;
       const bool trm = p.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 4 && j < 8;
       if (trm) p.trace[32 + (j - 4) * 8 + 0] = clock64();
-      // P_j is in shared memory and S_j has been consumed: S_{j+1} goes first so that the softmax warps can start
-      // on it while P_j V_j is still being issued / executed
-      mbar_wait(p_full, j & 1);
-      mbar_wait(s_empty, j & 1);
+      // S_{j+1} goes first (as soon as S_j has been read) so that the softmax warps find it ready when they finish
+      // tile j; P_j V_j follows once P_j is in shared memory
+      mbar_wait(s_empty, j & 1);          // arrives as soon as the softmax threads hold the last S_j chunk in registers
       if (trm) p.trace[32 + (j - 4) * 8 + 1] = clock64();
-      if (j + 1 < nkv) issue_s(j + 1);
+      if (j + 1 < nkv) issue_s(j + 1);    // overlaps the second half of the exp pass of tile j
       if (trm) p.trace[32 + (j - 4) * 8 + 2] = clock64();
+      mbar_wait(p_full, j & 1);
       // ---- O += P_j V_j (any rescaling of O for tile j happened before the p_full arrivals)
       if (trm) p.trace[32 + (j - 4) * 8 + 3] = clock64();
       tc_fence_after();
@@ -259,6 +259,10 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
         uint32_t v[32];
         tmem_ld32(tS + c * 32, v);
         tmem_ld_wait();
+        if (c == 1) {                     // S_j is fully consumed: the MMA warp may overwrite it with S_{j+1}
+          tc_fence_before();
+          mbar_arrive(s_empty);
+        }
         uint32_t pk[16];
         if (full_tile) {
 #pragma unroll
@@ -290,7 +294,6 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
       l += l0 + l1;
       if (trs) p.trace[(j - 4) * 8 + 5] = clock64();
       tc_fence_before();
-      mbar_arrive(s_empty);
       fence_proxy_async_smem();
       mbar_arrive(p_full);
       if (trs) p.trace[(j - 4) * 8 + 6] = clock64();

@@ -13,6 +13,8 @@
 #include "ur_common.cuh"
 #include "ur_host.h"
 
+#include <stdlib.h>
+
 namespace ur {
 
 constexpr int kGnThreads = 1024;
@@ -50,7 +52,7 @@ struct GnParams {
 };
 
 __global__ void __launch_bounds__(kGnThreads, 1) group_norm_cluster_kernel(const GnParams p) {
-  extern __shared__ float sh[];
+  extern __shared__ __align__(16) float sh[];
   const int C = p.C1 + p.C2;
   const int CL = static_cast<int>(cluster_nctarank());
   const int rank = static_cast<int>(cluster_ctarank());
@@ -59,13 +61,13 @@ __global__ void __launch_bounds__(kGnThreads, 1) group_norm_cluster_kernel(const
   float* s_sq = sh + C;              // [C]
   float* s_own = s_sq + C;           // [2 * G / CL]  (mean, rstd) of the groups this CTA owns
   float* s_grp = s_own + 2 * (p.G / CL);   // [2 * G]  all groups
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
 
   const int CV = C >> 3;
   const int PL = kGnThreads / CV;                      // pixel lanes (threads beyond CV * PL idle in the pixel loops)
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const bool active = pl < PL;
+  // [PL][2][C] per-pixel-lane partials, 16-byte aligned (shared-memory float atomics would serialise PL-fold)
+  float* s_part = sh + ((2 * C + 2 * (p.G / CL) + 2 * p.G + 3) & ~3);
   const int c0 = cv * 8;
   const int slab = (p.P + CL - 1) / CL;
   const int p0 = rank * slab;
@@ -98,11 +100,17 @@ __global__ void __launch_bounds__(kGnThreads, 1) group_norm_cluster_kernel(const
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_sum[c0 + j], s[j]);
-      atomicAdd(&s_sq[c0 + j], q[j]);
-    }
+    float* row = s_part + static_cast<size_t>(pl) * 2 * C + c0;
+    *reinterpret_cast<float4*>(row) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(row + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(row + C) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(row + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {      // [0, C): sums, [C, 2C): sums of squares (= s_sum | s_sq)
+    float t = 0.f;
+    for (int l = 0; l < PL; ++l) t += s_part[static_cast<size_t>(l) * 2 * C + i];
+    sh[i] = t;
   }
   cluster_sync_all();
 
@@ -201,7 +209,11 @@ static int probe_cluster(size_t smem_max) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, group_norm_cluster_kernel, &cfg) == cudaSuccess && n >= 4) best = 16;
+  // measured on B200 (tools/bench_norm.py): 16-CTA clusters are co-scheduled too sparsely (8 is 25-30 % faster), so the
+  // non-portable size is only used on request (ur_debug_set_group_norm_cluster)
+  if (cudaOccupancyMaxActiveClusters(&n, group_norm_cluster_kernel, &cfg) == cudaSuccess && n >= 8 &&
+      getenv("UR_GN_CLUSTER16"))
+    best = 16;
   cudaGetLastError();
   g_gn_cluster = best;
   return best;
@@ -211,10 +223,10 @@ static int probe_cluster(size_t smem_max) {
 
 using namespace ur;
 
-extern "C" int ur_group_norm_cluster_size(void) { return probe_cluster(48 * 1024); }
+extern "C" int ur_group_norm_cluster_size(void) { return probe_cluster(160 * 1024); }
 // development: override the cluster size (0 = probe again)
 extern "C" int ur_debug_set_group_norm_cluster(int n) {
-  probe_cluster(48 * 1024);
+  probe_cluster(160 * 1024);
   const int old = g_gn_cluster;
   g_gn_cluster = n > 0 ? n : 0;
   return old;
@@ -228,7 +240,7 @@ extern "C" int ur_group_norm(const void* x1, int64_t ld1, int64_t is1, int c1, c
   if (!x1 || !out || c1 <= 0 || c1 % 8 || c2 % 8 || (c2 && !x2) || groups <= 0 || C % groups || C > 8 * kGnThreads ||
       ld1 % 8 || ldo % 8 || (c2 && ld2 % 8) || batch <= 0 || pixels <= 0)
     return set_error(UR_ERR_ARG, "ur_group_norm: bad arguments (C=%d+%d groups=%d)", c1, c2, groups);
-  int CL = probe_cluster(48 * 1024);
+  int CL = probe_cluster(160 * 1024);
   while (CL > 1 && (groups % CL || pixels < CL)) CL >>= 1;
   GnParams p;
   p.x1 = static_cast<const bf16*>(x1);
@@ -248,8 +260,10 @@ extern "C" int ur_group_norm(const void* x1, int64_t ld1, int64_t is1, int c1, c
   p.out = static_cast<bf16*>(out);
   p.ldo = ldo;
   p.iso = iso;
-  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(C) + 2 * (groups / CL) + 2 * groups);
-  if (smem > 48 * 1024) return set_error(UR_ERR_ARG, "ur_group_norm: too many channels / groups (%d / %d)", C, groups);
+  const int PL = kGnThreads / (C >> 3);
+  const size_t smem = sizeof(float) * (2 * static_cast<size_t>(C) + 2 * (groups / CL) + 2 * groups + 8 +
+                                      2 * static_cast<size_t>(C) * PL);
+  if (smem > 160 * 1024) return set_error(UR_ERR_ARG, "ur_group_norm: too many channels / groups (%d / %d)", C, groups);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, batch, 1);
   cfg.blockDim = dim3(kGnThreads);

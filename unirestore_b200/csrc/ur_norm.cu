@@ -6,6 +6,8 @@
 #include "ur_common.cuh"
 #include "ur_host.h"
 
+#include <stdlib.h>
+
 namespace ur {
 
 // ------------------------------------------------------------------------------------ chan_stats
@@ -13,11 +15,10 @@ namespace ur {
 // and pixels p0+pl, p0+pl+PL, ...  fp32 per-thread partials -> shared fp32 atomics -> fp64 global atomics.
 __global__ void chan_stats_kernel(const bf16* __restrict__ x, long long ld, long long img_stride, int P, int C, int CV,
                                   int PL, int chunk, double* __restrict__ stats, int stats_ld, int stats_off) {
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ __align__(16) float sh[];  // [PL][2][C] per-pixel-lane partials (no shared-memory float atomics:
+                                               // they compile to CAS loops that serialise PL-fold per channel)
   const int b = blockIdx.y;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(P, p0 + chunk);
   float s[8], q[8];
@@ -44,16 +45,18 @@ __global__ void chan_stats_kernel(const bf16* __restrict__ x, long long ld, long
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sh[cv * 8 + j], s[j]);
-    atomicAdd(&sh[C + cv * 8 + j], q[j]);
-  }
+  float* row = sh + static_cast<size_t>(pl) * 2 * C + cv * 8;
+  *reinterpret_cast<float4*>(row) = make_float4(s[0], s[1], s[2], s[3]);
+  *reinterpret_cast<float4*>(row + 4) = make_float4(s[4], s[5], s[6], s[7]);
+  *reinterpret_cast<float4*>(row + C) = make_float4(q[0], q[1], q[2], q[3]);
+  *reinterpret_cast<float4*>(row + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
   __syncthreads();
   double* out = stats + (static_cast<long long>(b) * stats_ld + stats_off) * 2;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(out + 2 * c, static_cast<double>(sh[c]));
-    atomicAdd(out + 2 * c + 1, static_cast<double>(sh[C + c]));
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {      // i < C: sum of channel i, else sumsq of channel i - C
+    float t = 0.f;
+    for (int l = 0; l < PL; ++l) t += sh[static_cast<size_t>(l) * 2 * C + i];
+    const int c = i < C ? i : i - C;
+    atomicAdd(out + 2 * c + (i < C ? 0 : 1), static_cast<double>(t));
   }
 }
 
@@ -243,7 +246,8 @@ static void pick_block(int C, int P, int& CV, int& PL, int& chunk, int& nchunks,
   PL = CV >= 256 ? 1 : 256 / CV;
   if (PL < 1) PL = 1;
   // aim for ~4 waves of blocks over the GPU, at least 8 pixels per thread
-  const int target = max(1, (4 * num_sms()) / max(1, B));
+  static const int waves = getenv("UR_NORM_WAVES") ? atoi(getenv("UR_NORM_WAVES")) : 4;
+  const int target = max(1, (waves * num_sms()) / max(1, B));
   chunk = (P + target - 1) / target;
   const int min_chunk = PL * 8;
   if (chunk < min_chunk) chunk = min_chunk;
@@ -266,7 +270,7 @@ extern "C" int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int 
   int CV, PL, chunk, nchunks;
   pick_block(channels, pixels, CV, PL, chunk, nchunks, batch);
   dim3 grid(nchunks, batch);
-  chan_stats_kernel<<<grid, CV * PL, 2 * channels * sizeof(float), stream>>>(
+  chan_stats_kernel<<<grid, CV * PL, 2 * static_cast<size_t>(channels) * PL * sizeof(float), stream>>>(
       static_cast<const bf16*>(x), ld, img_stride, pixels, channels, CV, PL, chunk, stats, stats_ld, stats_off);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_chan_stats launch");

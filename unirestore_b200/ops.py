@@ -8,6 +8,7 @@ Nothing here falls back to PyTorch arithmetic: every op is one launch of a hand-
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -199,14 +200,18 @@ def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None
     return out
 
 
-FUSED_GN_MAX_BYTES = 96 << 20      # above this the tensor does not survive in L2 between the two passes
+# Tensors up to this size take the one-launch cluster kernel (ur_group_norm).  Measured on B200 (tools/bench_norm.py,
+# round 1): with 8-CTA clusters only 64 SMs stream the tensor and the kernel is 20-30 % SLOWER than ur_chan_stats +
+# ur_norm_apply on every per-step shape (16-CTA clusters are co-scheduled too sparsely and lose more), so it is off
+# by default; set UNIRESTORE_FUSED_GN_MB to route tensors up to that many MiB through it.
+FUSED_GN_MAX_BYTES = int(os.environ.get("UNIRESTORE_FUSED_GN_MB", "0")) << 20
 
 
 def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
     """nn.GroupNorm (+SiLU) over ``cat(x, x2)``.
 
-    L2-resident tensors (every per-step GroupNorm): ONE launch of the cluster kernel ``ur_group_norm`` (statistics
-    in distributed shared memory).  Larger tensors (VAE levels): ``ur_chan_stats`` (per source) + ``ur_norm_apply``."""
+    Default: ``ur_chan_stats`` (per source) + ``ur_norm_apply``.  Tensors up to ``FUSED_GN_MAX_BYTES`` take ONE launch
+    of the cluster kernel ``ur_group_norm`` (statistics in distributed shared memory) instead."""
     B, P, C1, ld1, is1 = _geom(x)
     C2 = x2.shape[-1] if x2 is not None else 0
     if B * P * (C1 + C2) * 2 <= FUSED_GN_MAX_BYTES and (C1 + C2) <= 8192:
