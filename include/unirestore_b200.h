@@ -88,6 +88,9 @@ typedef struct ur_conv_desc {
   int64_t res_sb, res_sy, res_sx;
   int act;             /* UR_ACT_* */
   int bn;              /* N tile: 0 = auto, else one of 64/128/160/256 (gated acts: caller packs for it) */
+  void* workspace;     /* optional caller-owned scratch (16-byte aligned) enabling split-K for problems with few output
+                          tiles and a long K (the UNet's 8x8 level): fp32 partial sums, 4*batch*hout*wout*n bytes */
+  int64_t workspace_bytes;
 } ur_conv_desc;
 
 int ur_conv_gemm(const ur_conv_desc* desc_host, void* stream);
@@ -99,6 +102,8 @@ int ur_debug_force_gemm_v1(int on);
 int ur_debug_set_gemm_trace(void* buf);
 /* Development: CTA-pair (tcgen05 cta_group::2) GEMM tiles: -1 auto (cost model), 0 never, 1 whenever legal. */
 int ur_debug_set_gemm_pair_mode(int mode);
+/* Development: 0 disables split-K (ur_conv_desc.workspace is then ignored); returns the previous value. */
+int ur_debug_set_gemm_splitk(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 
 /* ------------------------------------------------------------------------------------------------

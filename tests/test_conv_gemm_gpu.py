@@ -214,3 +214,27 @@ def test_gated_and_linear_pair_modes(pair_mode, mode):
         xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
         y = ops.conv_gemm(xb, wb, N, bias=b)
         assert_close(y, bf16_round(F.linear(xb.float(), wb.float(), b)), TOL, "linear pair=%d %s" % (mode, (M, K, N)))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 8, 8, 1280, 1280), (8, 8, 8, 2560, 1280), (3, 8, 8, 512, 512),
+                                            (1, 16, 16, 1280, 320)])
+def test_conv3x3_split_k(B, H, W, Cin, Cout):
+    """Few output tiles + long K: the K range is split over CTAs (fp32 red.global.add into the caller's workspace +
+    finishing kernel with bias / temb row vector / residual); compared with torch and with the unsplit kernel."""
+    from unirestore_b200 import _cabi, ops
+    x = _rand(B, Cin, H, W, seed=100)
+    w = _rand(Cout, Cin, 3, 3, seed=101, scale=(9 * Cin) ** -0.5)
+    b, tv = _rand(Cout, seed=102), _rand(1, Cout, seed=103)
+    r = _rand(B, H, W, Cout, seed=104).to(torch.bfloat16)
+    xb, wb = _nhwc(x), w.to(torch.bfloat16)
+    wp = ops.pack_conv_weight(wb)
+    y = ops.conv_gemm(xb, wp, Cout, taps=ops.TAPS_3x3, bias=b, rowvec=tv, residual=r)
+    ref = bf16_round((F.conv2d(xb.float().permute(0, 3, 1, 2), wb.float(), b, padding=1) + tv[0][None, :, None, None])
+                     .permute(0, 2, 3, 1) + r.float())
+    assert_close(y, ref, TOL, "conv3x3 split-K %s" % ((B, H, W, Cin, Cout),))
+    old = _cabi.lib().ur_debug_set_gemm_splitk(0)
+    try:
+        y0 = ops.conv_gemm(xb, wp, Cout, taps=ops.TAPS_3x3, bias=b, rowvec=tv, residual=r)
+    finally:
+        _cabi.lib().ur_debug_set_gemm_splitk(old)
+    assert_close(y, y0, 2e-3, "split-K vs unsplit")

@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ("chscale", C.c_void_p), ("chscale_sb", C.c_int64),
         ("residual", C.c_void_p), ("res_sb", C.c_int64), ("res_sy", C.c_int64), ("res_sx", C.c_int64),
         ("act", C.c_int), ("bn", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -52,6 +53,7 @@ SIGNATURES = {
     "ur_debug_force_gemm_v1": (C.c_int, [C.c_int]),
     "ur_debug_set_gemm_trace": (C.c_int, [_P]),
     "ur_debug_set_gemm_pair_mode": (C.c_int, [C.c_int]),
+    "ur_debug_set_gemm_splitk": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_trace": (C.c_int, [_P]),
     "ur_chan_stats": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _I, _I, _P]),
     "ur_group_norm": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _I, _I, _I, _P, _P, _F, _I, _P, _I64, _I64, _P]),

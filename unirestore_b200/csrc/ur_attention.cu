@@ -90,6 +90,8 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_T = tmem_base + 128;
 
@@ -354,8 +356,7 @@ static int launch_attention(const AttnParams& p, const CUtensorMap& mq, const CU
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention)");
     configured = true;
   }
-  attention_kernel<D><<<grid, 320, smem, stream>>>(p, mq, mk, mv);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(attention_kernel<D>, grid, dim3(320), smem, stream, p, mq, mk, mv);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention launch");
 }
 

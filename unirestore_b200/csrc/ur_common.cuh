@@ -36,6 +36,14 @@ __device__ __forceinline__ bool elect_one_sync() {
 template <typename T>
 __device__ __forceinline__ T warp_uniform(T v) { return __shfl_sync(0xffffffffu, v, 0); }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization (ur_host.h launch_kernel): the
+// next kernel in the stream / graph may start while this one drains, runs its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, shared-memory setup) and then blocks in pdl_wait() until the predecessor has
+// completed and its writes are visible.  Rule: NO global-memory access before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -211,7 +219,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_ma
 // ------------------------------------------------------------------ math
 // x * sigmoid(x) with MUFU ex2 + MUFU rcp (relative error ~1e-6, far below the bf16 rounding of the result)
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (nn.GELU() default, GEGLU).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16
+// rounding of the result): branch-free, 2 MUFU (ex2, rcp) + ~12 FP32 ops instead of the ~40-instruction branchy erff
+// (the GEGLU epilogue evaluates 16 384 of these per 128x256 accumulator tile and was bound by it).
+__device__ __forceinline__ float erf_as_f(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float y = fmaf(-p * t, __expf(-ax * ax), 1.0f);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752f)); }
+
+// 16-byte vector reduction into global memory (sm_90+): four fp32 adds in one L2 atomic transaction
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

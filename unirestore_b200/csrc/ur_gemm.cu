@@ -72,6 +72,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     // =============================== TMA producer (whole warp; the elected lane issues) ===============================
@@ -254,8 +256,7 @@ static int launch_conv_gemm(const GemmParams& p, const CUtensorMap& a1, const CU
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm)");
     configured = true;
   }
-  conv_gemm_kernel<BN, STAGES, MINB><<<grid, 192, smem, stream>>>(p, a1, a2, w);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(conv_gemm_kernel<BN, STAGES, MINB>, grid, dim3(192), smem, stream, p, a1, a2, w);
   if (e != cudaSuccess) return set_cuda_error(e, "conv_gemm launch");
   return UR_OK;
 }
@@ -297,6 +298,12 @@ extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
 // Measured model of the main loop (cycles per 64-deep k-block): the UMMA itself 2*bn (128 rows per SM), the
 // shared-memory traffic of TMA write + UMMA read, (16 KB + W bytes) * 2 / 128 B per cycle, and ~75 cycles of issue
 // per tcgen05.mma.  A pair stages only bn/2 weight rows per CTA.
+static int g_split_mode = getenv("UR_GEMM_SPLITK") ? atoi(getenv("UR_GEMM_SPLITK")) : 1;   // 0: never split K
+extern "C" int ur_debug_set_gemm_splitk(int on) {
+  const int old = g_split_mode;
+  g_split_mode = on;
+  return old;
+}
 static int g_pair_mode = getenv("UR_GEMM_PAIR") ? atoi(getenv("UR_GEMM_PAIR")) : -1;   // -1 auto, 0 never, 1 whenever legal
 extern "C" int ur_debug_set_gemm_pair_mode(int mode) {
   const int old = g_pair_mode;
@@ -375,10 +382,24 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   if (best_cost < 0) return set_error(UR_ERR_ARG, "ur_conv_gemm: no tile shape");
   const int Wt = 1 << best_w, Ht = 1 << best_h, Bt = 128 >> (best_w + best_h);
 
+  // ---- split-K candidates: few output tiles and a long K (the UNet / Controller 8x8 level: 4 M tiles, up to 360
+  //      k-blocks).  Wide pair tiles keep the per-k-block efficiency; the K range is then cut so that the units fill the
+  //      GPU, partial sums meet in the caller's fp32 workspace (red.global.add.v4.f32) and splitk_finish applies the
+  //      epilogue.  Needs: plain epilogue (bias / temb row vector / residual), bf16 output, workspace large enough.
+  const int nkb_total = d->ntaps * (((d->group_kc ? d->group_kc : ctot) + 63) / 64);
+  const long long m_rows = static_cast<long long>(d->batch) * d->hout * d->wout;
+  const bool split_ok = g_split_mode != 0 && d->workspace && !(reinterpret_cast<uintptr_t>(d->workspace) & 15) && !gated &&
+                        d->act == UR_ACT_NONE && d->alpha == 1.0f && !d->chscale && !d->w_batched && !d->group_kc &&
+                        d->out_dtype == UR_DT_BF16 && d->n % 8 == 0 && !d->bn && best_cost <= 8 && nkb_total >= 64 &&
+                        4LL * m_rows * d->n <= d->workspace_bytes;
   int bn = 0;
   bool pair = false;
   pick_tile_config(d->n, best_cost, d->ntaps * (((d->group_kc ? d->group_kc : ctot) + 63) / 64), d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : 0),
                    !d->w_batched && best_cost >= 2, &bn, &pair);
+  if (split_ok) {
+    bn = d->n % 160 == 0 ? 160 : 128;
+    pair = best_cost >= 2 && g_pair_mode != 0;
+  }
   if (bn != 64 && bn != 128 && bn != 160 && bn != 256) return set_error(UR_ERR_ARG, "ur_conv_gemm: bad N tile");
   if (gated && (d->n % bn)) return set_error(UR_ERR_ARG, "ur_conv_gemm: gated act needs n %% bn == 0");
   int kc = ctot;
@@ -430,6 +451,8 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   p.res_sx = d->res_sx;
   p.act = d->act;
   p.trace = g_trace;
+  p.ksplit = 1;
+  p.ws = nullptr;
 
   // ---- fast path (persistent kernel): bf16 output with 16-byte aligned pitches
   const int n_out = gated ? d->n / 2 : d->n;
@@ -483,6 +506,22 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * tiles_b;
     const long long total = static_cast<long long>(n_tiles) * (pair_path ? (m_tiles + 1) / 2 : m_tiles);
     if (total > 0x7fffffffLL) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many tiles");
+    p.ksplit = 1;
+    if (split_ok) {
+      const long long ctas = pair_path ? 2 * total : total;
+      int s = static_cast<int>(num_sms() / (ctas > 0 ? ctas : 1));
+      if (s > nkb_total / 16) s = nkb_total / 16;
+      if (s > 8) s = 8;
+      if (s >= 2) {
+        p.ksplit = s;
+        p.ws = static_cast<float*>(d->workspace);
+        cudaError_t e = cudaMemsetAsync(d->workspace, 0, 4ULL * m_rows * d->n, stream);
+        if (e != cudaSuccess) return set_cuda_error(e, "ur_conv_gemm split-K memset");
+        int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, pair_path, bn, static_cast<int>(total * s), n_tiles, stream);
+        if (rc) return rc;
+        return launch_splitk_finish(p, stream);
+      }
+    }
     return launch_conv_gemm_persistent(p, mA1, mA2, mW, pair_path, bn, static_cast<int>(total), n_tiles, stream);
   }
 

@@ -29,6 +29,8 @@ struct GemmParams {
   const bf16* residual;
   long long res_sb, res_sy, res_sx;
   int act;
+  int ksplit;         // split-K factor (1 = off); work unit u -> (tile u / ksplit, K slice u % ksplit)
+  float* ws;          // split-K: dense fp32 [B*Ho*Wo, N] partial sums (red.global.add), epilogue deferred to splitk_finish
   long long* trace;   // development: per-role clock64 timestamps of CTA 0 (nullptr = off)
 };
 
@@ -38,6 +40,8 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 
 // persistent kernel entry (ur_gemm_persistent.cu).  pair = true: CTA pairs with tcgen05.mma.cta_group::2 on 256 x bn
 // tiles (w: tensor map with bn/2-row boxes, total_units = pair tiles); else one CTA per 128 x bn tile.
+// split-K epilogue: out = bf16(ws + bias + rowvec + residual) (ur_gemm_persistent.cu)
+int launch_splitk_finish(const GemmParams& p, cudaStream_t stream);
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
                                 bool pair, int bn, int total_units, int n_tiles, cudaStream_t stream);
 

@@ -87,12 +87,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   const int Wt = 1 << p.wt_log2, Ht = 1 << p.ht_log2;
   const int Bt = kBlockM >> (p.wt_log2 + p.ht_log2);
   const int nkb = p.ntaps * p.cblocks;
+  const int ksplit = p.ksplit;
   // scheduling: work units (tiles, or 256-row pair tiles) are dealt round-robin to CTAs (or CTA pairs)
   const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : -1;
   const int u_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int u_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
-  if (tracing && threadIdx.x == 0) p.trace[7 * 16] = clock64();
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA1);
@@ -122,17 +122,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   if constexpr (PAIR) cluster_sync_all();               // peer barriers initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  if (tracing && threadIdx.x == 0) p.trace[7 * 16 + 1] = clock64();
+  pdl_launch_dependents();
+  pdl_wait();                      // prologue done; from here on global memory written by the predecessor is read
+  if (tracing && threadIdx.x == 0) p.trace[7 * 16] = p.trace[7 * 16 + 1] = clock64();
 
   if (warp < kNumAProd) {
     // =============================== activation TMA producers (whole warp, elected lane issues) ===============
     int kiter = 0, it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
+      const int tile = t / ksplit, ks = t - tile * ksplit;
+      const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;          // this unit's K slice (split-K)
+      const TileCoord tc = tile_coord(p, tile, n_tiles, BN, Wt, Ht, Bt, rank);
       const int cbase = p.group_kc ? (tc.n0 / p.group_nc) * p.group_kc : 0;
       if (tracing && lane == 0 && warp == 0 && it < 8) p.trace[0 * 16 + it] = clock64();
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < nkb; ++kb, ++kiter) {
+      int tap = kb0 / p.cblocks, cb = kb0 % p.cblocks;
+      for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumAProd == warp) {
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
@@ -170,11 +174,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     const int me = warp - kNumAProd;
     int kiter = 0, it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
+      const int tile = t / ksplit, ks = t - tile * ksplit;
+      const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
+      const TileCoord tc = tile_coord(p, tile, n_tiles, BN, Wt, Ht, Bt, rank);
       const int wb = p.w_batched ? tc.b0 : 0;
       const int wrow = PAIR ? tc.n0 + rank * (BN / 2) : tc.n0;     // PAIR: this CTA stages half of the N rows
-      int tap = 0, cb = 0;
-      for (int kb = 0; kb < nkb; ++kb, ++kiter) {
+      int tap = kb0 / p.cblocks, cb = kb0 % p.cblocks;
+      for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumWProd == me) {
           const int s = kiter % STAGES;
           const uint32_t ph = (kiter / STAGES) & 1;
@@ -215,10 +221,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         // Two k-blocks per iteration: the fixed cost of one trip through the issue path (barrier test, fence, elect,
         // commit: ~250 cycles measured) is paid once per 8 MMAs.  The full-barrier tests of the NEXT two k-blocks are
         // issued before the MMAs of the current ones so that their ~50-100 cycle latency is off the issue path.
+        const int ks = t % ksplit;
+        const int nk = (ks + 1) * nkb / ksplit - ks * nkb / ksplit;      // k-blocks of this unit
         bool ready0 = mbar_test_wait(&full_bar[stage], phase);
         bool ready1 = false;
-        for (int kb = 0; kb < nkb; kb += 2) {
-          const bool two = kb + 1 < nkb;
+        for (int kb = 0; kb < nk; kb += 2) {
+          const bool two = kb + 1 < nk;
           const bool trk = tracing && lane == 0 && it == 1 && kb >= 8 && kb < 40;
           if (trk) p.trace[128 + 4 * ((kb - 8) >> 1)] = clock64();
           const uint32_t s0 = stage, ph0 = phase;
@@ -245,8 +253,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
               n1 = 0;
               nph1 ^= 1;
             }
-            ready0 = (kb + 2 < nkb) ? mbar_test_wait(&full_bar[stage], phase) : false;
-            ready1 = (kb + 3 < nkb) ? mbar_test_wait(&full_bar[n1], nph1) : false;
+            ready0 = (kb + 2 < nk) ? mbar_test_wait(&full_bar[stage], phase) : false;
+            ready1 = (kb + 3 < nk) ? mbar_test_wait(&full_bar[n1], nph1) : false;
           }
           const uint32_t alo0 = a_lo0 + s0 * (kStageBytes >> 4);           // (smem address >> 4) of the A tiles
           const uint32_t alo1 = a_lo0 + s1 * (kStageBytes >> 4);
@@ -287,7 +295,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     float a_nx = 0.f, m_nx = 1.f;                 // this thread's column of the NEXT tile's add / mul vectors
     auto fetch_vec = [&](int tt) {
-      const TileCoord tn = tile_coord(p, tt, n_tiles, BN, Wt, Ht, Bt, rank);
+      const TileCoord tn = tile_coord(p, tt / ksplit, n_tiles, BN, Wt, Ht, Bt, rank);
       const int n = tn.n0 + et;
       const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
       const int bb = tn.b0 < p.B ? tn.b0 : p.B - 1;      // (a PAIR ghost tile lies past the last image)
@@ -302,9 +310,36 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     if (et < BN && u_first < total_tiles) fetch_vec(u_first);
     int it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
+      const TileCoord tc = tile_coord(p, t / ksplit, n_tiles, BN, Wt, Ht, Bt, rank);
       const int nout0 = gated ? (tc.n0 >> 1) : tc.n0;
       const int as = it & 1;
+      if (p.ws) {
+        // ---- split-K: add this unit's fp32 partial tile into the workspace (vector reductions, 16 B each); bias /
+        //      residual / bf16 conversion happen once in splitk_finish_kernel
+        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+        const int x = tc.x0 + (r & (Wt - 1)), y = tc.y0 + ((r >> p.wt_log2) & (Ht - 1));
+        const int b = tc.b0 + (r >> (p.wt_log2 + p.ht_log2));
+        const bool ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+        float* wrow = p.ws + (static_cast<long long>(b * p.Ho + y) * p.Wo + x) * p.N + tc.n0;
+        for (int c = grp * 32; c < BN; c += 64) {
+          uint32_t va[32];
+          tmem_ld32(trow + c, va);
+          tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (tc.n0 + c + 4 * j + 4 <= p.N)
+                red_add_v4_f32(wrow + c + 4 * j, __uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                               __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
+            }
+          }
+        }
+        tc_fence_before();
+        if constexpr (PAIR) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
+        continue;
+      }
       // ---- stage the per-column add / mul vectors of this tile (double-buffered by `as`); the values were
       //      fetched one tile ahead so their global-load latency hides behind the previous tile's epilogue
       float* add = s_add + as * BN;
@@ -455,6 +490,53 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   }
 }
 
+// out[b, y, x, n] = bf16(ws[m, n] + bias[n] + rowvec[b, n] + residual[b, y, x, n]); 8 channels per thread
+__global__ void splitk_finish_kernel(const GemmParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nv = p.N >> 3;
+  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * nv;
+  bf16* outp = reinterpret_cast<bf16*>(p.out);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % nv);
+    const long long m = i / nv;
+    const int x = static_cast<int>(m % p.Wo);
+    const int y = static_cast<int>((m / p.Wo) % p.Ho);
+    const int b = static_cast<int>(m / (static_cast<long long>(p.Wo) * p.Ho));
+    const float4 a0 = *reinterpret_cast<const float4*>(p.ws + m * p.N + cv * 8);
+    const float4 a1 = *reinterpret_cast<const float4*>(p.ws + m * p.N + cv * 8 + 4);
+    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = cv * 8 + j;
+      if (p.bias) f[j] += __ldg(p.bias + n);
+      if (p.rowvec) f[j] += __ldg(p.rowvec + b * p.rowvec_sb + n);
+    }
+    if (p.residual) {
+      const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + b * p.res_sb + y * p.res_sy + x * p.res_sx + cv * 8));
+      const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float r0, r1;
+        unpack_bf16(u[k], r0, r1);
+        f[2 * k] += r0;
+        f[2 * k + 1] += r1;
+      }
+    }
+    *reinterpret_cast<uint4*>(outp + b * p.out_sb + y * p.out_sy + x * p.out_sx + cv * 8) =
+        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+}
+
+int launch_splitk_finish(const GemmParams& p, cudaStream_t stream) {
+  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * (p.N >> 3);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
+  cudaError_t e = launch_kernel(splitk_finish_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p);
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "splitk_finish launch");
+}
+
 template <int BN, bool PAIR>
 static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
                     int total_units, int n_tiles, cudaStream_t stream) {
@@ -475,13 +557,15 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_persistent_kernel<BN, PAIR>, p, a1, a2, w, total_units, n_tiles);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "conv_gemm_persistent launch");
 }

@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace ur {
 
@@ -68,6 +69,14 @@ int encode_tensor_map(CUtensorMap* map, void* base, int rank, const uint64_t* di
 }
 
 int num_sms() { return g_num_sms ? g_num_sms : 148; }
+
+int pdl_enabled() {
+  static const int on = []() {
+    const char* e = getenv("UR_PDL");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return on;
+}
 
 }  // namespace ur
 

@@ -37,6 +37,8 @@ __device__ float block_reduce(float v, bool is_max, float* sh) {
 // ------------------------------------------------------------------------------------ softmax_rows
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, bf16* __restrict__ p, long long ldp,
                                     int n_valid, int n_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   const long long row = blockIdx.x;
   const float* sr = s + row * lds;
@@ -55,6 +57,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long long lds, 
 // ------------------------------------------------------------------------------------ transpose_tokens
 __global__ void transpose_tokens_kernel(const bf16* __restrict__ x, long long ld, long long bs, int T, int D,
                                         bf16* __restrict__ out, int Tpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ bf16 tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -75,6 +79,8 @@ __global__ void transpose_tokens_kernel(const bf16* __restrict__ x, long long ld
 __global__ void dwconv3x3_gate_kernel(const bf16* __restrict__ x, int H, int W, int c, const float* __restrict__ wgt,
                                       const float* __restrict__ bias, bf16* __restrict__ y, double* __restrict__ stats,
                                       int CV, int PL, int chunk) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float sh[];  // pooled[c] | weights transposed to [9][2c] (tap-major, 128-bit reads)
   const int C2 = 2 * c;
   float* s_pool = sh;
@@ -164,6 +170,8 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 __global__ void small_linear_kernel(const void* __restrict__ x, int in_mode, float in_scale, long long x_ld,
                                     const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y,
                                     long long y_ld, int B, int N, int K, int groups, int act_in, int act_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (gw >= static_cast<long long>(B) * N) return;
@@ -188,6 +196,8 @@ __global__ void small_linear_kernel(const void* __restrict__ x, int in_mode, flo
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos(t f_i), sin(t f_i)],
 // f_i = exp(-ln(10000) * i / half)   (base_model.py:104, controller.py:86,196)
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -205,6 +215,8 @@ __global__ void adanaf_scales_kernel(const double* __restrict__ stats, float inv
                                      const float* __restrict__ wi, const float* __restrict__ bi,
                                      const float* __restrict__ wg, const float* __restrict__ bg,
                                      float* __restrict__ scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // m[C4], intra[C4], inter[G]
   float* m = sh;
   float* intra = sh + C4;
@@ -238,6 +250,8 @@ __global__ void tfa_gates_kernel(const double* __restrict__ stats, float inv_p, 
                                  const float* __restrict__ cond, const float* __restrict__ w_out,
                                  const float* __restrict__ b_out, const float* __restrict__ w_pt,
                                  const float* __restrict__ b_pt, float* __restrict__ o, float* __restrict__ cond_next) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // pooled[3*T*D], newc[T*D], red[32]
   const int hid = T * D;
   float* pooled = sh;
@@ -299,6 +313,8 @@ __device__ __forceinline__ void store_nhwc8(bf16* dst, float v0, float v1, float
 // autoencoder.py:152-155 (DiagonalGaussianDistribution.sample * scaling_factor); moments: fp32 [B,h,w,8] (mean|logvar)
 __global__ void posterior_sample_kernel(const float* __restrict__ moments, const float* __restrict__ noise, float sf,
                                         long long hw, long long total, float* __restrict__ z, bf16* __restrict__ z8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / hw, p = i % hw;
@@ -321,6 +337,8 @@ __global__ void posterior_sample_kernel(const float* __restrict__ moments, const
 __global__ void latent_axpby_kernel(const float* __restrict__ x, float a, const float* __restrict__ y, float bcoef,
                                     long long hw, long long total, float* __restrict__ out, bf16* __restrict__ out8,
                                     float scale8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / hw, p = i % hw;
@@ -341,6 +359,8 @@ __global__ void latent_axpby_kernel(const float* __restrict__ x, float a, const 
 __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict__ eps, int ld_eps, float sqrt_at,
                                  float sqrt_1mat, float sqrt_ap, float sqrt_1map, int clip, long long hw,
                                  long long total, bf16* __restrict__ x8) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long b = i / hw, p = i % hw;
@@ -363,6 +383,8 @@ __global__ void ddim_step_kernel(float* __restrict__ x, const float* __restrict_
 __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy,
                                       long long sx, int C, int H, int W, float a, float bofs, long long total,
                                       bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int xx = static_cast<int>(i % W);
@@ -379,6 +401,8 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long s
 // unifie.py:164)
 __global__ void nhwc_to_image_kernel(const float* __restrict__ src, int ld, int Hs, int Ws, int C, int H, int W,
                                      float a, float bofs, long long total, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int xx = static_cast<int>(i % W);
@@ -412,7 +436,7 @@ extern "C" int ur_softmax_rows(const float* scores, int64_t ld_s, void* probs, i
   if (!scores || !probs || rows <= 0 || n_valid <= 0 || n_pad < n_valid)
     return set_error(UR_ERR_ARG, "ur_softmax_rows: bad arguments");
   const int threads = n_valid >= 1024 ? 256 : (n_valid >= 128 ? 128 : 32);
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
       scores, ld_s, static_cast<bf16*>(probs), ld_p, n_valid, n_pad);
   UR_LAUNCH_CHECK("ur_softmax_rows");
 }
@@ -421,7 +445,7 @@ extern "C" int ur_transpose_tokens(const void* x, int64_t ld, int64_t batch_stri
                                    void* out, int tokens_pad, void* stream) {
   if (!x || !out || tokens_pad < tokens) return set_error(UR_ERR_ARG, "ur_transpose_tokens: bad arguments");
   dim3 grid((tokens_pad + 31) / 32, (dim + 31) / 32, batch);
-  transpose_tokens_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(transpose_tokens_kernel, dim3(grid), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const bf16*>(x), ld, batch_stride, tokens, dim, static_cast<bf16*>(out), tokens_pad);
   UR_LAUNCH_CHECK("ur_transpose_tokens");
 }
@@ -440,7 +464,7 @@ extern "C" int ur_dwconv3x3_gate(const void* x, int batch, int h, int w, int c, 
   int chunk = (P + target - 1) / target;
   if (chunk < PL * 2) chunk = PL * 2;
   dim3 grid((P + chunk - 1) / chunk, batch);
-  dwconv3x3_gate_kernel<<<grid, CV * PL, (c + 18 * static_cast<size_t>(c)) * sizeof(float), stream>>>(static_cast<const bf16*>(x), h, w, c, weight, bias,
+  launch_kernel(dwconv3x3_gate_kernel, dim3(grid), dim3(CV * PL), (c + 18 * static_cast<size_t>(c)) * sizeof(float), stream, static_cast<const bf16*>(x), h, w, c, weight, bias,
                                                                      static_cast<bf16*>(y), stats, CV, PL, chunk);
   UR_LAUNCH_CHECK("ur_dwconv3x3_gate");
 }
@@ -452,7 +476,7 @@ extern "C" int ur_small_linear(const void* x, int in_mode, float in_scale, int64
   const long long warps = static_cast<long long>(batch) * n;
   const int block = 256;
   const unsigned grid = static_cast<unsigned>((warps * 32 + block - 1) / block);
-  small_linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, in_mode, in_scale, x_ld, w, bias, y, y_ld,
+  launch_kernel(small_linear_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), x, in_mode, in_scale, x_ld, w, bias, y, y_ld,
                                                                             batch, n, k, groups, act_in, act_out);
   UR_LAUNCH_CHECK("ur_small_linear");
 }
@@ -460,7 +484,7 @@ extern "C" int ur_small_linear(const void* x, int in_mode, float in_scale, int64
 extern "C" int ur_timestep_embedding(const int64_t* timesteps, int batch, int dim, float* out, void* stream) {
   if (!timesteps || !out || dim % 2) return set_error(UR_ERR_ARG, "ur_timestep_embedding: bad arguments");
   const int total = batch * dim / 2;
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const long long*>(timesteps), batch, dim, out);
   UR_LAUNCH_CHECK("ur_timestep_embedding");
 }
@@ -470,7 +494,7 @@ extern "C" int ur_adanaf_scales(const double* stats, int pixels, int batch, int 
                                 void* stream) {
   if (!stats || !scale || c4 % groups) return set_error(UR_ERR_ARG, "ur_adanaf_scales: bad arguments");
   const size_t sh = (2 * static_cast<size_t>(c4) + groups) * sizeof(float);
-  adanaf_scales_kernel<<<batch, 256, sh, static_cast<cudaStream_t>(stream)>>>(stats, 1.0f / pixels, c4, groups, w_intra,
+  launch_kernel(adanaf_scales_kernel, dim3(batch), dim3(256), sh, static_cast<cudaStream_t>(stream), stats, 1.0f / pixels, c4, groups, w_intra,
                                                                              b_intra, w_inter, b_inter, scale);
   UR_LAUNCH_CHECK("ur_adanaf_scales");
 }
@@ -482,7 +506,7 @@ extern "C" int ur_tfa_gates(const double* stats, int pixels, int batch, int prom
     return set_error(UR_ERR_ARG, "ur_tfa_gates: bad arguments");
   const size_t sh = (4 * static_cast<size_t>(prompt_len) * dim + 32) * sizeof(float);
   if (sh > 48 * 1024) return set_error(UR_ERR_ARG, "ur_tfa_gates: prompt too large");
-  tfa_gates_kernel<<<batch, 256, sh, static_cast<cudaStream_t>(stream)>>>(stats, 1.0f / pixels, prompt_len, dim, cond,
+  launch_kernel(tfa_gates_kernel, dim3(batch), dim3(256), sh, static_cast<cudaStream_t>(stream), stats, 1.0f / pixels, prompt_len, dim, cond,
                                                                          w_out, b_out, w_pt, b_pt, o, cond_next);
   UR_LAUNCH_CHECK("ur_tfa_gates");
 }
@@ -491,7 +515,7 @@ extern "C" int ur_posterior_sample(const float* moments, const float* noise, flo
                                    float* z, void* z_nhwc8, void* stream) {
   if (!moments || !noise || !z) return set_error(UR_ERR_ARG, "ur_posterior_sample: bad arguments");
   const long long total = static_cast<long long>(batch) * hw;
-  posterior_sample_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(posterior_sample_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       moments, noise, scaling_factor, hw, total, z, static_cast<bf16*>(z_nhwc8));
   UR_LAUNCH_CHECK("ur_posterior_sample");
 }
@@ -500,7 +524,7 @@ extern "C" int ur_latent_axpby(const float* x, float a, const float* y, float b,
                                void* out_nhwc8, float scale8, void* stream) {
   if (!x || (!out && !out_nhwc8)) return set_error(UR_ERR_ARG, "ur_latent_axpby: bad arguments");
   const long long total = static_cast<long long>(batch) * hw;
-  latent_axpby_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(latent_axpby_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, a, y, b, hw, total, out, static_cast<bf16*>(out_nhwc8), scale8);
   UR_LAUNCH_CHECK("ur_latent_axpby");
 }
@@ -510,7 +534,7 @@ extern "C" int ur_ddim_step(float* x, const float* eps, int ld_eps, float sqrt_a
                             void* x_nhwc8, void* stream) {
   if (!x || !eps || ld_eps < 4) return set_error(UR_ERR_ARG, "ur_ddim_step: bad arguments");
   const long long total = static_cast<long long>(batch) * hw;
-  ddim_step_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_kernel(ddim_step_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, eps, ld_eps, sqrt_alpha_t, sqrt_one_minus_alpha_t, sqrt_alpha_prev, sqrt_one_minus_alpha_prev, clip_sample, hw,
       total, static_cast<bf16*>(x_nhwc8));
   UR_LAUNCH_CHECK("ur_ddim_step");
@@ -520,7 +544,7 @@ extern "C" int ur_image_to_nhwc8(const float* img, int64_t sb, int64_t sc, int64
                                  int channels, int h, int w, float a, float b, void* out, void* stream) {
   if (!img || !out || channels > 8) return set_error(UR_ERR_ARG, "ur_image_to_nhwc8: bad arguments");
   const long long total = static_cast<long long>(batch) * h * w;
-  image_to_nhwc8_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, sb, sc, sy, sx, channels, h,
+  launch_kernel(image_to_nhwc8_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), img, sb, sc, sy, sx, channels, h,
                                                                                        w, a, b, total,
                                                                                        static_cast<bf16*>(out));
   UR_LAUNCH_CHECK("ur_image_to_nhwc8");
@@ -530,7 +554,7 @@ extern "C" int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int ba
                                 float a, float b, float* out, void* stream) {
   if (!src || !out || h > hs || w > ws || channels > ld) return set_error(UR_ERR_ARG, "ur_nhwc_to_image: bad arguments");
   const long long total = static_cast<long long>(batch) * channels * h * w;
-  nhwc_to_image_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, ld, hs, ws, channels, h, w, a,
+  launch_kernel(nhwc_to_image_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, ld, hs, ws, channels, h, w, a,
                                                                                       b, total, out);
   UR_LAUNCH_CHECK("ur_nhwc_to_image");
 }

@@ -15,6 +15,8 @@ namespace ur {
 // and pixels p0+pl, p0+pl+PL, ...  fp32 per-thread partials -> shared fp32 atomics -> fp64 global atomics.
 __global__ void chan_stats_kernel(const bf16* __restrict__ x, long long ld, long long img_stride, int P, int C, int CV,
                                   int PL, int chunk, double* __restrict__ stats, int stats_ld, int stats_off) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) float sh[];  // [PL][2][C] per-pixel-lane partials (no shared-memory float atomics:
                                                // they compile to CAS loops that serialise PL-fold per channel)
   const int b = blockIdx.y;
@@ -66,6 +68,8 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
                                   const double* __restrict__ stats, int G, int P, int CV, int PL, int chunk,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                   bf16* __restrict__ out, long long ldo, long long iso) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sh[];  // mean[G], rstd[G]
   const int C = C1 + C2;
   const int cg = C / G;
@@ -137,6 +141,8 @@ template <int NV, int R>
 __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
                                  int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= M) return;
@@ -220,6 +226,8 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
 // ------------------------------------------------------------------------------------ scale_channels
 __global__ void scale_channels_kernel(bf16* __restrict__ x, long long ld, long long img_stride, int P, int CV,
                                       const float* __restrict__ s, int s_ld) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const long long total = static_cast<long long>(P) * CV;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -270,7 +278,7 @@ extern "C" int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int 
   int CV, PL, chunk, nchunks;
   pick_block(channels, pixels, CV, PL, chunk, nchunks, batch);
   dim3 grid(nchunks, batch);
-  chan_stats_kernel<<<grid, CV * PL, 2 * static_cast<size_t>(channels) * PL * sizeof(float), stream>>>(
+  launch_kernel(chan_stats_kernel, dim3(grid), dim3(CV * PL), 2 * static_cast<size_t>(channels) * PL * sizeof(float), stream, 
       static_cast<const bf16*>(x), ld, img_stride, pixels, channels, CV, PL, chunk, stats, stats_ld, stats_off);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_chan_stats launch");
@@ -288,7 +296,7 @@ extern "C" int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, c
   int CV, PL, chunk, nchunks;
   pick_block(C, pixels, CV, PL, chunk, nchunks, batch);
   dim3 grid(nchunks, batch);
-  norm_apply_kernel<<<grid, CV * PL, 2 * groups * sizeof(float), stream>>>(
+  launch_kernel(norm_apply_kernel, dim3(grid), dim3(CV * PL), 2 * groups * sizeof(float), stream, 
       static_cast<const bf16*>(x1), ld1, is1, c1, static_cast<const bf16*>(x2), ld2, is2, c2, stats, groups, pixels, CV,
       PL, chunk, gamma, beta, eps, silu, static_cast<bf16*>(out), ldo, iso);
   cudaError_t e = cudaGetLastError();
@@ -308,13 +316,13 @@ extern "C" int ur_layernorm(const void* x, int64_t ldx, void* out, int64_t ldo, 
   const int M = static_cast<int>(rows);
   auto blocks = [&](int r) { return static_cast<unsigned>((rows + static_cast<int64_t>(warps) * r - 1) / (warps * r)); };
   if (channels <= 256)
-    layernorm_kernel<1, 4><<<blocks(4), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    launch_kernel(layernorm_kernel<1, 4>, dim3(blocks(4)), dim3(warps * 32), 0, stream, xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   else if (channels <= 512)
-    layernorm_kernel<2, 4><<<blocks(4), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    launch_kernel(layernorm_kernel<2, 4>, dim3(blocks(4)), dim3(warps * 32), 0, stream, xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   else if (channels <= 1280)
-    layernorm_kernel<5, 2><<<blocks(2), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    launch_kernel(layernorm_kernel<5, 2>, dim3(blocks(2)), dim3(warps * 32), 0, stream, xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   else
-    layernorm_kernel<8, 1><<<blocks(1), warps * 32, 0, stream>>>(xp, ldx, op, ldo, M, channels, gamma, beta, eps);
+    launch_kernel(layernorm_kernel<8, 1>, dim3(blocks(1)), dim3(warps * 32), 0, stream, xp, ldx, op, ldo, M, channels, gamma, beta, eps);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_layernorm launch");
 }
@@ -330,7 +338,7 @@ extern "C" int ur_scale_channels(void* x, int64_t ld, int64_t img_stride, int ba
   if (gxl > 8LL * num_sms()) gxl = 8LL * num_sms();
   int gx = static_cast<int>(gxl);
   if (gx < 1) gx = 1;
-  scale_channels_kernel<<<dim3(gx, batch), 256, 0, stream>>>(static_cast<bf16*>(x), ld, img_stride, pixels, CV, scale,
+  launch_kernel(scale_channels_kernel, dim3(dim3(gx, batch)), dim3(256), 0, stream, static_cast<bf16*>(x), ld, img_stride, pixels, CV, scale,
                                                            scale_ld);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_scale_channels launch");

@@ -39,6 +39,8 @@ class DiffUIE(nn.Module):
             self.scheduler = DDIMScheduler.from_pretrained("stabilityai/sd-turbo", subfolder="scheduler")
             self.scheduler.set_timesteps(cnet["num_inference_steps"], device=self.train_timesteps.device)
         self._temb_cache = {}
+        self._side_streams = {}
+        self.overlap_controller = os.environ.get("UNIRESTORE_OVERLAP_CONTROLLER", "1") == "1"
         # CUDA-graph replay of the whole forward for static shapes (one capture per (shape, task, noise-mode));
         # every kernel behind the C-ABI is capture-safe (no allocation, no synchronisation).
         self.use_cuda_graph = os.environ.get("UNIRESTORE_CUDA_GRAPH", "0") == "1"
@@ -78,10 +80,24 @@ class DiffUIE(nn.Module):
             if hasattr(m, "invalidate"):
                 m.invalidate()
 
+    def _run_controller(self, z0_8, t: int):
+        emb_c, _ = self._embeddings(t, z0_8.device)
+        ops.stats_arena_begin(z0_8.device, "ctl")    # one fill instead of a memset node per GroupNorm
+        try:
+            return self.controller.run(z0_8, emb_c)                              # unifie.py:148
+        finally:
+            ops.stats_arena_end(z0_8.device)
+
+    def _run_unet(self, zt8, control, t: int):
+        _, emb_u = self._embeddings(t, zt8.device)
+        ops.stats_arena_begin(zt8.device)
+        try:
+            return self.base_model.run(zt8, control, emb_u)                      # unifie.py:149
+        finally:
+            ops.stats_arena_end(zt8.device)
+
     def predict_eps(self, zt8, z0_8, t: int):
-        emb_c, emb_u = self._embeddings(t, zt8.device)
-        control = self.controller.run(z0_8, emb_c)                               # unifie.py:148
-        return self.base_model.run(zt8, control, emb_u)                          # unifie.py:149
+        return self._run_unet(zt8, self._run_controller(z0_8, t), t)
 
     def predict_z0(self, latents, conditions, timesteps):                        # unifie.py:91-105
         ts = sorted(set(int(t) for t in timesteps.reshape(-1).tolist()))
@@ -101,9 +117,40 @@ class DiffUIE(nn.Module):
             noise = torch.randn_like(z0)
         sa, sb = self.ddpm.noise_coefficients(999)                               # unifie.py:141-144
         zt, zt8 = ops.latent_axpby(z0, sa, noise.float().contiguous(), sb, want_nhwc8=True)
-        for t in self.scheduler.timesteps_host:                                  # unifie.py:146-150
-            eps8 = self.predict_eps(zt8, z0_8, t)
+        # The Controller only depends on (z0, t): the one of step i+1 runs on a side stream concurrently with the UNet
+        # of step i and fills the SMs its many small, dependent kernels leave idle (tails / prologues / underfilled
+        # grids).  Its outputs are kept alive until the loop ends, so no buffer crosses streams while being recycled.
+        ts = [int(t) for t in self.scheduler.timesteps_host]
+        main = torch.cuda.current_stream(z0.device)
+        side = self._side_streams.get(z0.device)
+        if side is None:
+            side = self._side_streams[z0.device] = torch.cuda.Stream(device=z0.device)
+        overlap = self.overlap_controller and len(ts) > 1
+        keep = []
+
+        def launch_controller(i):
+            if not overlap:
+                return self._run_controller(z0_8, ts[i]), None
+            if i == 0:
+                side.wait_stream(main)                                            # z0_8 is produced on the main stream
+            with torch.cuda.stream(side):
+                ctl = self._run_controller(z0_8, ts[i])
+                ev = torch.cuda.Event()
+                ev.record(side)
+            keep.append(ctl)
+            return ctl, ev
+
+        nxt = launch_controller(0)
+        for i, t in enumerate(ts):                                               # unifie.py:146-150
+            control, ev = nxt
+            if i + 1 < len(ts):
+                nxt = launch_controller(i + 1)
+            if ev is not None:
+                main.wait_event(ev)
+            eps8 = self._run_unet(zt8, control, t)
             zt8 = ops.ddim_step_(zt, eps8, self.scheduler.step_coefficients(t), bool(self.scheduler.config.clip_sample))
+        if overlap:
+            main.wait_stream(side)
         return zt
 
     @torch.no_grad()

@@ -52,6 +52,20 @@ def _check_nhwc(t, name):
     return ld
 
 
+_WS = {}
+_ROLE = ["main"]      # which execution context issues the calls: "main" or "ctl" (the Controller's side stream)
+
+
+def _workspace(device, nbytes=16 << 20):
+    """Caller-owned split-K scratch handed to every ur_conv_gemm call: one per (device, role), since the Controller
+    of the next DDIM step runs on a side stream concurrently with the UNet (stream-ordered reuse within a stream)."""
+    key = (device, _ROLE[0])
+    ws = _WS.get(key)
+    if ws is None:
+        ws = _WS[key] = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+    return ws
+
+
 def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None, bias=None, rowvec=None,
               chscale=None, residual=None, act=UR_ACT_NONE, alpha=1.0, out=None, out_dtype=torch.bfloat16,
               group_kc=0, group_nc=0, w_batched=False, bn=0):
@@ -123,6 +137,8 @@ def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None
         d.residual = r.data_ptr()
         d.res_sb, d.res_sy, d.res_sx = r.stride(0), r.stride(1), r.stride(2)
     d.act, d.bn = act, bn
+    ws = _workspace(x.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     _cabi.ensure_init(x.device.index or 0)
     check(_cabi.lib().ur_conv_gemm(C.byref(d), _stream()), "ur_conv_gemm")
     return ret
@@ -172,12 +188,57 @@ def _f32(t, name):
 
 
 # ----------------------------------------------------------------------------------------------- normalisation
+class _StatsArena:
+    """Pool of pre-zeroed fp64 statistics buffers: ONE fill per DDIM step instead of one memset node per GroupNorm
+    (108 per step).  The used prefix (high-water mark of the previous pass) is what gets zeroed.  One pool per
+    (device, role): the Controller runs on a side stream."""
+
+    def __init__(self):
+        self.buf, self.off, self.hwm, self.active = None, 0, 0, False
+
+
+_ARENAS = {}
+
+
+def _arena_for(device):
+    key = (device, _ROLE[0])
+    a = _ARENAS.get(key)
+    if a is None:
+        a = _ARENAS[key] = _StatsArena()
+    return a
+
+
+def stats_arena_begin(device, role="main", capacity=32 << 20):
+    """Enter execution context ``role`` (selects the split-K workspace and statistics pool) and zero the pool."""
+    _ROLE[0] = role
+    a = _arena_for(device)
+    if a.buf is None:
+        a.buf, a.hwm = torch.empty(capacity // 8, dtype=torch.float64, device=device), 0
+    n = a.hwm if a.hwm else a.buf.numel()
+    a.buf[:n].zero_()
+    a.off, a.active = 0, True
+
+
+def stats_arena_end(device):
+    a = _arena_for(device)
+    a.hwm, a.active = max(a.hwm, a.off), False
+    _ROLE[0] = "main"
+
+
 def chan_stats(x, stats=None, offset=0, total_channels=None, zero=True):
     """fp64 (sum, sumsq) per (image, channel) -> ``[B, total_channels, 2]``."""
     B, P, Cc, ld, ist = _geom(x)
     total = total_channels or Cc
     if stats is None:
-        stats = torch.empty((B, total, 2), device=x.device, dtype=torch.float64)
+        a, n = _arena_for(x.device), B * total * 2
+        # the zeroed prefix is [0, hwm) (the whole pool on the first pass)
+        if a.active and a.off + n <= (a.hwm if a.hwm else a.buf.numel()):
+            stats, zero = a.buf[a.off:a.off + n].view(B, total, 2), False
+            a.off += n
+        else:
+            if a.active:
+                a.off += n          # grows the high-water mark for the next pass
+            stats = torch.empty((B, total, 2), device=x.device, dtype=torch.float64)
     check(_lib().ur_chan_stats(_ptr(x), ld, ist, B, P, Cc, _ptr(stats), total, offset, int(zero), _stream()),
           "ur_chan_stats")
     return stats
@@ -207,6 +268,9 @@ def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None
 FUSED_GN_MAX_BYTES = int(os.environ.get("UNIRESTORE_FUSED_GN_MB", "0")) << 20
 
 
+_ABLATE = set(filter(None, os.environ.get("UR_ABLATE", "").split(",")))   # development: time-share ablations (WRONG results)
+
+
 def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
     """nn.GroupNorm (+SiLU) over ``cat(x, x2)``.
 
@@ -214,6 +278,11 @@ def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
     of the cluster kernel ``ur_group_norm`` (statistics in distributed shared memory) instead."""
     B, P, C1, ld1, is1 = _geom(x)
     C2 = x2.shape[-1] if x2 is not None else 0
+    if "gn" in _ABLATE and B * P * (C1 + C2) * 2 <= (96 << 20):
+        return x if x2 is None else torch.empty(tuple(x.shape[:-1]) + (C1 + C2,), device=x.device, dtype=x.dtype)
+    if "gnstats" in _ABLATE and B * P * (C1 + C2) * 2 <= (96 << 20):
+        st = torch.zeros((B, C1 + C2, 2), device=x.device, dtype=torch.float64) + 1.0
+        return norm_apply(x, st, groups, gamma, beta, eps, silu, x2)
     if B * P * (C1 + C2) * 2 <= FUSED_GN_MAX_BYTES and (C1 + C2) <= 8192:
         ld2, is2 = 0, 0
         if x2 is not None:
@@ -233,6 +302,8 @@ def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
 
 
 def layernorm(x, gamma, beta, eps):
+    if "ln" in _ABLATE:
+        return x
     B, P, Cc, ld, ist = _geom(x)
     if B > 1 and ist != P * ld:
         raise ValueError("layernorm needs a dense token matrix")
@@ -275,6 +346,8 @@ def attention(q, k, v, heads, out=None):
     512-wide head) take the unfused GEMM -> softmax -> GEMM path."""
     B, Tq, Cc = q.shape
     d = Cc // heads
+    if "attn" in _ABLATE and d in (64, 128):
+        return q if q.is_contiguous() else q.contiguous()
     if d not in (64, 128):
         return attention_unfused(q, k, v, heads, out)
     Tk = k.shape[1]
