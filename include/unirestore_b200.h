@@ -104,6 +104,8 @@ int ur_debug_set_gemm_trace(void* buf);
 int ur_debug_set_gemm_pair_mode(int mode);
 /* Development: 0 disables split-K (ur_conv_desc.workspace is then ignored); returns the previous value. */
 int ur_debug_set_gemm_splitk(int on);
+/* Development: 0 = persistent-kernel epilogue stores with st.global instead of TMA; returns the previous value. */
+int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 
 /* ------------------------------------------------------------------------------------------------

@@ -252,6 +252,22 @@ __device__ __forceinline__ void unpack_bf16(uint32_t u, float& a, float& b) {
 
 }  // namespace ur
 
+namespace ur {
+// ------------------------------------------------------------------ TMA store (shared -> global, bulk async group)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups may still be READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+}  // namespace ur
+
 // ------------------------------------------------------------------ 2-CTA (cta_group::2) variants
 // A CTA pair (cluster of 2 on one TPC) runs ONE tcgen05.mma of M = 256: each CTA supplies its own 128 rows of A and
 // half of the N rows of B from its own shared memory and receives its 128 accumulator rows in its own TMEM.  Only

@@ -298,6 +298,12 @@ extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
 // Measured model of the main loop (cycles per 64-deep k-block): the UMMA itself 2*bn (128 rows per SM), the
 // shared-memory traffic of TMA write + UMMA read, (16 KB + W bytes) * 2 / 128 B per cycle, and ~75 cycles of issue
 // per tcgen05.mma.  A pair stages only bn/2 weight rows per CTA.
+static int g_tma_store = getenv("UR_GEMM_TMA_STORE") ? atoi(getenv("UR_GEMM_TMA_STORE")) : 1;   // 0: st.global epilogue
+extern "C" int ur_debug_set_gemm_tma_store(int on) {
+  const int old = g_tma_store;
+  g_tma_store = on;
+  return old;
+}
 static int g_split_mode = getenv("UR_GEMM_SPLITK") ? atoi(getenv("UR_GEMM_SPLITK")) : 1;   // 0: never split K
 extern "C" int ur_debug_set_gemm_splitk(int on) {
   const int old = g_split_mode;
@@ -453,6 +459,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   p.trace = g_trace;
   p.ksplit = 1;
   p.ws = nullptr;
+  p.tma_store = 0;
 
   // ---- fast path (persistent kernel): bf16 output with 16-byte aligned pitches
   const int n_out = gated ? d->n / 2 : d->n;
@@ -502,11 +509,29 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   }
 
   if (fast_path) {
+    // output tensor map for the TMA-store epilogue: (n_out, Wo, Ho, B) with the caller's strides (channel-slice and
+    // sub-pixel phase views included), box (32 ch, Wt, Ht, Bt) = one 128 x 64 B staging buffer, 64-byte swizzle
+    CUtensorMap mO = mA1;
+    p.tma_store = 0;
+    if (g_tma_store) {
+      const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(d->wout), static_cast<uint64_t>(d->hout),
+                                static_cast<uint64_t>(d->batch)};
+      const uint64_t str[3] = {static_cast<uint64_t>(d->out_sx) * 2, static_cast<uint64_t>(d->out_sy) * 2,
+                               static_cast<uint64_t>(d->out_sb) * 2};
+      const uint32_t box[4] = {32u, static_cast<uint32_t>(Wt), static_cast<uint32_t>(Ht), static_cast<uint32_t>(Bt)};
+      const uint32_t es[4] = {1u, 1u, 1u, 1u};
+      const bool str_ok = d->out_sx > 0 && (d->hout == 1 || d->out_sy > 0) && (d->batch == 1 || d->out_sb > 0);
+      if (str_ok && encode_tensor_map(&mO, d->out, 4, dims, str, box, es, 64) == UR_OK) p.tma_store = 1;
+    }
     const int n_tiles = (d->n + bn - 1) / bn;
     const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * tiles_b;
     const long long total = static_cast<long long>(n_tiles) * (pair_path ? (m_tiles + 1) / 2 : m_tiles);
-    if (total > 0x7fffffffLL) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many tiles");
+    if (total > 0x3fffffffLL) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many tiles");
     p.ksplit = 1;
+    p.fd_ntiles = make_fastdiv(static_cast<uint32_t>(n_tiles));
+    p.fd_ksplit = make_fastdiv(1);
+    p.fd_tx = make_fastdiv(static_cast<uint32_t>(p.tiles_x));
+    p.fd_ty = make_fastdiv(static_cast<uint32_t>(p.tiles_y));
     if (split_ok) {
       const long long ctas = pair_path ? 2 * total : total;
       int s = static_cast<int>(num_sms() / (ctas > 0 ? ctas : 1));
@@ -514,15 +539,16 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
       if (s > 8) s = 8;
       if (s >= 2) {
         p.ksplit = s;
+        p.fd_ksplit = make_fastdiv(static_cast<uint32_t>(s));
         p.ws = static_cast<float*>(d->workspace);
         cudaError_t e = cudaMemsetAsync(d->workspace, 0, 4ULL * m_rows * d->n, stream);
         if (e != cudaSuccess) return set_cuda_error(e, "ur_conv_gemm split-K memset");
-        int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, pair_path, bn, static_cast<int>(total * s), n_tiles, stream);
+        int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total * s), n_tiles, stream);
         if (rc) return rc;
         return launch_splitk_finish(p, stream);
       }
     }
-    return launch_conv_gemm_persistent(p, mA1, mA2, mW, pair_path, bn, static_cast<int>(total), n_tiles, stream);
+    return launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total), n_tiles, stream);
   }
 
   dim3 grid((d->n + bn - 1) / bn, p.tiles_x * p.tiles_y * tiles_b, 1);

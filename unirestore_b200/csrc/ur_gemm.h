@@ -6,6 +6,31 @@
 
 namespace ur {
 
+// Division by a run-time constant without the ~25-instruction IDIV sequence: q = umulhi(x, mul) >> shr (x < 2^31).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  if (d <= 1) {
+    f.mul = 0;
+    f.shr = 0;
+    return f;
+  }
+  uint32_t lg = 0;
+  while ((1u << lg) < d) ++lg;                       // ceil(log2(d))
+  const uint32_t p = 31 + lg;
+  f.mul = static_cast<uint32_t>(((1ull << p) + d - 1) / d);
+  f.shr = p - 32;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int fast_div(int x, const FastDiv& f) {
+  return f.d <= 1 ? x : static_cast<int>(__umulhi(static_cast<uint32_t>(x), f.mul) >> f.shr);
+}
+#endif
+
 struct GemmParams {
   int B, Ho, Wo, N;
   int cblocks;         // 64-channel blocks per tap
@@ -15,6 +40,7 @@ struct GemmParams {
   unsigned long long dy_pack, dx_pack;  // 4 bits per tap, value+8
   int wt_log2, ht_log2;                 // M tile = Wt x Ht x Bt pixels, Wt*Ht*Bt = 128
   int tiles_x, tiles_y;
+  FastDiv fd_ntiles, fd_ksplit, fd_tx, fd_ty;   // fast division by n_tiles / ksplit / tiles_x / tiles_y (persistent kernel)
   int group_kc, group_nc;
   int w_batched;
   void* out;
@@ -29,6 +55,7 @@ struct GemmParams {
   const bf16* residual;
   long long res_sb, res_sy, res_sx;
   int act;
+  int tma_store;      // persistent kernel: 1 = epilogue sub-blocks leave through TMA stores (mapOut), 0 = coalesced st.global
   int ksplit;         // split-K factor (1 = off); work unit u -> (tile u / ksplit, K slice u % ksplit)
   float* ws;          // split-K: dense fp32 [B*Ho*Wo, N] partial sums (red.global.add), epilogue deferred to splitk_finish
   long long* trace;   // development: per-role clock64 timestamps of CTA 0 (nullptr = off)
@@ -43,6 +70,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 // split-K epilogue: out = bf16(ws + bias + rowvec + residual) (ur_gemm_persistent.cu)
 int launch_splitk_finish(const GemmParams& p, cudaStream_t stream);
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                                bool pair, int bn, int total_units, int n_tiles, cudaStream_t stream);
+                                const CUtensorMap& mo, bool pair, int bn, int total_units, int n_tiles,
+                                cudaStream_t stream);
 
 }  // namespace ur

@@ -19,8 +19,11 @@
 
 namespace ur {
 
-constexpr int kEpiPitch = 80;                        // 32 bf16 + 16 B pad: conflict-free row-wise 16-byte writes
-constexpr int kEpiStageBytes = kBlockM * kEpiPitch;  // per epilogue warp group
+// Epilogue staging: per warp group TWO buffers of 128 rows x 64 B (32 bf16) in the TMA 64-byte-swizzle layout
+// (16-byte chunk index ^= (row >> 1) & 3): conflict-free row-wise 16-byte writes AND the box layout of the TMA store.
+constexpr int kEpiBufBytes = kBlockM * 64;           // 8 KB
+constexpr int kEpiStageBytes = 2 * kEpiBufBytes;     // per epilogue warp group
+__device__ __forceinline__ int stg_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 constexpr int kNumAProd = 3, kNumWProd = 2;
 constexpr int kMmaWarp = kNumAProd + kNumWProd;      // 5
 constexpr int kEpiWarp0 = kMmaWarp + 1;              // 6
@@ -47,14 +50,14 @@ struct TileCoord {
 __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int n_tiles, int BN, int Wt, int Ht, int Bt,
                                                 int pair_rank) {
   TileCoord c;
-  const int nt = u % n_tiles;
-  int mt = u / n_tiles;
+  int mt = fast_div(u, p.fd_ntiles);
+  const int nt = u - mt * n_tiles;
   if (pair_rank >= 0) mt = 2 * mt + pair_rank;
   c.n0 = nt * BN;
-  const int tx = mt % p.tiles_x;
-  mt /= p.tiles_x;
-  const int ty = mt % p.tiles_y;
-  const int tb = mt / p.tiles_y;
+  const int q1 = fast_div(mt, p.fd_tx);
+  const int tx = mt - q1 * p.tiles_x;
+  const int tb = fast_div(q1, p.fd_ty);
+  const int ty = q1 - tb * p.tiles_y;
   c.x0 = tx * Wt;
   c.y0 = ty * Ht;
   c.b0 = tb * Bt;
@@ -67,7 +70,7 @@ template <int BN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap mapA1,
                             const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW,
-                            int total_tiles, int n_tiles) {
+                            const __grid_constant__ CUtensorMap mapOut, int total_tiles, int n_tiles) {
   using Cfg = PCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::kStages;
   constexpr int kStageBytes = Cfg::kStageBytes;
@@ -98,6 +101,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapA2);
     tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapOut);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -130,12 +134,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     // =============================== activation TMA producers (whole warp, elected lane issues) ===============
     int kiter = 0, it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const int tile = t / ksplit, ks = t - tile * ksplit;
-      const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;          // this unit's K slice (split-K)
+      const int tile = fast_div(t, p.fd_ksplit), ks = t - tile * ksplit;
+      const int kb0 = fast_div(ks * nkb, p.fd_ksplit), kb1 = fast_div((ks + 1) * nkb, p.fd_ksplit);          // this unit's K slice (split-K)
       const TileCoord tc = tile_coord(p, tile, n_tiles, BN, Wt, Ht, Bt, rank);
       const int cbase = p.group_kc ? (tc.n0 / p.group_nc) * p.group_kc : 0;
       if (tracing && lane == 0 && warp == 0 && it < 8) p.trace[0 * 16 + it] = clock64();
-      int tap = kb0 / p.cblocks, cb = kb0 % p.cblocks;
+      int tap = 0, cb = 0;
+      if (kb0) {                                   // split-K slices start mid-way
+        tap = kb0 / p.cblocks;
+        cb = kb0 - tap * p.cblocks;
+      }
       for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumAProd == warp) {
           const int s = kiter % STAGES;
@@ -174,12 +182,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     const int me = warp - kNumAProd;
     int kiter = 0, it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const int tile = t / ksplit, ks = t - tile * ksplit;
-      const int kb0 = ks * nkb / ksplit, kb1 = (ks + 1) * nkb / ksplit;
+      const int tile = fast_div(t, p.fd_ksplit), ks = t - tile * ksplit;
+      const int kb0 = fast_div(ks * nkb, p.fd_ksplit), kb1 = fast_div((ks + 1) * nkb, p.fd_ksplit);
       const TileCoord tc = tile_coord(p, tile, n_tiles, BN, Wt, Ht, Bt, rank);
       const int wb = p.w_batched ? tc.b0 : 0;
       const int wrow = PAIR ? tc.n0 + rank * (BN / 2) : tc.n0;     // PAIR: this CTA stages half of the N rows
-      int tap = kb0 / p.cblocks, cb = kb0 % p.cblocks;
+      int tap = 0, cb = 0;
+      if (kb0) {                                   // split-K slices start mid-way
+        tap = kb0 / p.cblocks;
+        cb = kb0 - tap * p.cblocks;
+      }
       for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumWProd == me) {
           const int s = kiter % STAGES;
@@ -221,8 +233,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         // Two k-blocks per iteration: the fixed cost of one trip through the issue path (barrier test, fence, elect,
         // commit: ~250 cycles measured) is paid once per 8 MMAs.  The full-barrier tests of the NEXT two k-blocks are
         // issued before the MMAs of the current ones so that their ~50-100 cycle latency is off the issue path.
-        const int ks = t % ksplit;
-        const int nk = (ks + 1) * nkb / ksplit - ks * nkb / ksplit;      // k-blocks of this unit
+        const int ks = t - fast_div(t, p.fd_ksplit) * ksplit;
+        const int nk = fast_div((ks + 1) * nkb, p.fd_ksplit) - fast_div(ks * nkb, p.fd_ksplit);      // k-blocks of this unit
         bool ready0 = mbar_test_wait(&full_bar[stage], phase);
         bool ready1 = false;
         for (int kb = 0; kb < nk; kb += 2) {
@@ -290,12 +302,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     // cooperative phase: thread gt moves 16-byte chunk (gt & 3) of rows (gt >> 2) + 32 i, i = 0..3
     const int cchunk = gt & 3;
     const int crow0 = gt >> 2;
-    uint8_t* stg = staging + grp * kEpiStageBytes;
-    uint8_t* srow = stg + r * kEpiPitch;
+    uint8_t* const stg_base = staging + grp * kEpiStageBytes;
+    int sbuf = 0;                                 // staging buffer of the next sub-block (alternates)
+    const bool use_tma = p.tma_store != 0;
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     float a_nx = 0.f, m_nx = 1.f;                 // this thread's column of the NEXT tile's add / mul vectors
     auto fetch_vec = [&](int tt) {
-      const TileCoord tn = tile_coord(p, tt / ksplit, n_tiles, BN, Wt, Ht, Bt, rank);
+      const TileCoord tn = tile_coord(p, fast_div(tt, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
       const int n = tn.n0 + et;
       const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
       const int bb = tn.b0 < p.B ? tn.b0 : p.B - 1;      // (a PAIR ghost tile lies past the last image)
@@ -310,7 +323,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     if (et < BN && u_first < total_tiles) fetch_vec(u_first);
     int it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const TileCoord tc = tile_coord(p, t / ksplit, n_tiles, BN, Wt, Ht, Bt, rank);
+      const TileCoord tc = tile_coord(p, fast_div(t, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
       const int nout0 = gated ? (tc.n0 >> 1) : tc.n0;
       const int as = it & 1;
       if (p.ws) {
@@ -351,16 +364,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         if (tn < total_tiles) fetch_vec(tn);
       }
       // global element offsets of the 4 rows this thread moves in the cooperative phases (-1: outside the tensor)
-      long long coff[4], roff[4];
+      long long roff[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rr = crow0 + 32 * i;
         const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
         const int b = tc.b0 + (rr >> (p.wt_log2 + p.ht_log2));
         const bool ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-        coff[i] = ok ? (b * p.out_sb + y * p.out_sy + x * p.out_sx + nout0) : -1;
         roff[i] = ok ? (b * p.res_sb + y * p.res_sy + x * p.res_sx + nout0) : -1;
       }
+      auto ooff = [&](int i) {                    // output offset of cooperative row i (non-TMA store path only)
+        const int rr = crow0 + 32 * i;
+        const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
+        const int b = tc.b0 + (rr >> (p.wt_log2 + p.ht_log2));
+        return b * p.out_sb + y * p.out_sy + x * p.out_sx + nout0;
+      };
       // residual of this group's first sub-block, fetched (coalesced) while the main loop still runs
       uint4 rres[4];
       int c = grp * 32;
@@ -379,18 +397,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       tc_fence_after();
       const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
 
-      for (; c < ncols; c += 64) {
+      for (; c < ncols; c += 64, sbuf ^= 1) {
         const bool tre = tracing && it == 1 && et == 0 && c < 192;
         if (tre) p.trace[320 + (c >> 6) * 8] = clock64();
+        uint8_t* stg = stg_base + sbuf * kEpiBufBytes;
         uint32_t va[32];
         tmem_ld32(trow + c, va);
-        // (A) staging tile is free again; park the prefetched residual chunk in it
+        // (A) this staging buffer is free again: the TMA store issued from it two sub-blocks ago has read it
+        if (use_tma && gt == 0) bulk_wait_group_read<1>();
         group_barrier(2 + grp);
         if (tre) p.trace[320 + (c >> 6) * 8 + 1] = clock64();
         if (p.residual) {
+          // park the prefetched (coalesced) residual chunk in the staging buffer
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(stg + (crow0 + 32 * i) * kEpiPitch + cchunk * 16) = rres[i];
+            *reinterpret_cast<uint4*>(stg + stg_off(crow0 + 32 * i, cchunk)) = rres[i];
           group_barrier(4 + grp);
           // prefetch the residual of this group's next sub-block
           const int cn = c + 64;
@@ -431,10 +452,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
             f[j] = has_mul ? v * mul[c + j] : v;
           }
         }
-        // own row: (+ residual) -> bf16 -> staging
+        // own row: (+ residual) -> bf16 -> staging (swizzled)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4* sp = reinterpret_cast<uint4*>(srow + j * 16);
+          uint4* sp = reinterpret_cast<uint4*>(stg + stg_off(r, j));
           if (p.residual) {
             const uint4 rv = *sp;
             const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -450,25 +471,34 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
                            pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
         }
         if (tre) p.trace[320 + (c >> 6) * 8 + 3] = clock64();
-        group_barrier(6 + grp);
-        if (tre) p.trace[320 + (c >> 6) * 8 + 4] = clock64();
-        // (C) coalesced write-out: a warp stores 8 rows x 64 contiguous bytes per instruction
-        {
+        if (use_tma) {
+          // (C) one TMA store per sub-block: the box (32 ch, Wt, Ht, Bt) is clipped against the output tensor
+          fence_proxy_async_smem();                 // generic-proxy writes above -> visible to the async proxy
+          group_barrier(6 + grp);
+          if (tre) p.trace[320 + (c >> 6) * 8 + 4] = clock64();
+          if (gt == 0) {
+            tma_store_4d(&mapOut, stg, nout0 + c, tc.x0, tc.y0, tc.b0);
+            bulk_commit_group();
+          }
+        } else {
+          group_barrier(6 + grp);
+          if (tre) p.trace[320 + (c >> 6) * 8 + 4] = clock64();
+          // (C) coalesced write-out: a warp stores 8 rows x 64 contiguous bytes per instruction
           const int col = c + cchunk * 8;
           if (nout0 + col + 8 <= n_out) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if (coff[i] >= 0)
-                *reinterpret_cast<uint4*>(outp + coff[i] + col) =
-                    *reinterpret_cast<const uint4*>(stg + (crow0 + 32 * i) * kEpiPitch + cchunk * 16);
+              if (roff[i] >= 0)
+                *reinterpret_cast<uint4*>(outp + ooff(i) + col) =
+                    *reinterpret_cast<const uint4*>(stg + stg_off(crow0 + 32 * i, cchunk));
             }
           } else if (nout0 + col < n_out) {               // ragged channel tail (n_out % 8 != 0 never reaches here)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if (coff[i] >= 0) {
-                const bf16* sv = reinterpret_cast<const bf16*>(stg + (crow0 + 32 * i) * kEpiPitch + cchunk * 16);
+              if (roff[i] >= 0) {
+                const bf16* sv = reinterpret_cast<const bf16*>(stg + stg_off(crow0 + 32 * i, cchunk));
                 for (int k = 0; k < 8; ++k)
-                  if (nout0 + col + k < n_out) outp[coff[i] + col + k] = sv[k];
+                  if (nout0 + col + k < n_out) outp[ooff(i) + col + k] = sv[k];
               }
             }
           }
@@ -479,6 +509,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       if constexpr (PAIR) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
       if (tracing && it < 8 && et == 0) p.trace[6 * 16 + it] = clock64();
     }
+    if (use_tma && gt == 0) bulk_wait_group_all();      // shared memory must outlive the last TMA stores
   }
 
   tc_fence_before();
@@ -539,7 +570,7 @@ int launch_splitk_finish(const GemmParams& p, cudaStream_t stream) {
 
 template <int BN, bool PAIR>
 static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                    int total_units, int n_tiles, cudaStream_t stream) {
+                    const CUtensorMap& mo, int total_units, int n_tiles, cudaStream_t stream) {
   using Cfg = PCfg<BN, PAIR>;
   constexpr int smem = Cfg::kSmem;
   static_assert(smem <= 227 * 1024 && Cfg::kStages >= 3, "shared memory budget");
@@ -566,25 +597,26 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_persistent_kernel<BN, PAIR>, p, a1, a2, w, total_units, n_tiles);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_persistent_kernel<BN, PAIR>, p, a1, a2, w, mo, total_units, n_tiles);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "conv_gemm_persistent launch");
 }
 
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                                bool pair, int bn, int total_units, int n_tiles, cudaStream_t stream) {
+                                const CUtensorMap& mo, bool pair, int bn, int total_units, int n_tiles,
+                                cudaStream_t stream) {
   if (pair) {
     switch (bn) {
-      case 64: return launch_p<64, true>(p, a1, a2, w, total_units, n_tiles, stream);
-      case 128: return launch_p<128, true>(p, a1, a2, w, total_units, n_tiles, stream);
-      case 160: return launch_p<160, true>(p, a1, a2, w, total_units, n_tiles, stream);
-      default: return launch_p<256, true>(p, a1, a2, w, total_units, n_tiles, stream);
+      case 64: return launch_p<64, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      case 128: return launch_p<128, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      case 160: return launch_p<160, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      default: return launch_p<256, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
     }
   }
   switch (bn) {
-    case 64: return launch_p<64, false>(p, a1, a2, w, total_units, n_tiles, stream);
-    case 128: return launch_p<128, false>(p, a1, a2, w, total_units, n_tiles, stream);
-    case 160: return launch_p<160, false>(p, a1, a2, w, total_units, n_tiles, stream);
-    default: return launch_p<256, false>(p, a1, a2, w, total_units, n_tiles, stream);
+    case 64: return launch_p<64, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    case 128: return launch_p<128, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    case 160: return launch_p<160, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    default: return launch_p<256, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
   }
 }
 
