@@ -165,7 +165,9 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------ ours
 def kernel_roofline(dev):
     """The dominant kernel (tcgen05 implicit-GEMM conv, UNet 320->320 3x3 @64x64, B=8: 60.4 GFLOP per launch)
-    timed alone with CUDA events on the launching stream; operands rotate over 8 buffer sets (> L2)."""
+    timed alone with CUDA events on the launching stream; operands rotate over 8 buffer sets (> L2).
+    ``traffic`` = dram__bytes_read.sum + dram__bytes_write.sum of that launch from the committed ncu --set full
+    capture (profiles/ncu_r1f_gemm_unet320.txt: 22.89 MB + 0.14 MB; the output stays in L2 within the capture)."""
     from unirestore_b200 import ops
     B, H, W, C = 8, 64, 64, 320
     sets = []
@@ -195,7 +197,7 @@ def kernel_roofline(dev):
     peak = float(peaks.get("bf16_tflops", 1590.0))
     ach = flops / t / 1e12
     return {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": 22.88e6, "kernel": "ur::conv_gemm_persistent_kernel<160> conv3x3 320->320 @64x64 B=8",
+            "traffic": 23.03e6, "kernel": "ur::conv_gemm_persistent_kernel<160, PAIR> conv3x3 320->320 @64x64 B=8",
             "launch_us": t * 1e6, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback"}
 
 

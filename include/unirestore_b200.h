@@ -88,6 +88,10 @@ typedef struct ur_conv_desc {
   int64_t res_sb, res_sy, res_sx;
   int act;             /* UR_ACT_* */
   int bn;              /* N tile: 0 = auto, else one of 64/128/160/256 (gated acts: caller packs for it) */
+  double* stats;       /* optional: per-(image, output channel) (sum, sumsq) of the bf16 OUTPUT are ACCUMULATED into
+                          stats[(b * stats_ld + stats_off + n) * 2 + {0,1}] (caller zeroes it): the statistics pass of
+                          the GroupNorm that consumes this output, fused into the epilogue (ur_chan_stats layout) */
+  int stats_ld, stats_off;
   void* workspace;     /* optional caller-owned scratch (16-byte aligned) enabling split-K for problems with few output
                           tiles and a long K (the UNet's 8x8 level): fp32 partial sums, 4*batch*hout*wout*n bytes */
   int64_t workspace_bytes;
@@ -117,9 +121,11 @@ int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
  * and nn.AdaptiveAvgPool2d(1) (nafnet_arch.py:62, cfrm.py:24,30, taskeditor.py:35,44,53). */
 int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int batch, int pixels, int channels, double* stats,
                   int stats_ld, int stats_off, int zero_first, void* stream);
-/* out = [silu]( (cat(x1,x2) - mean_g) * rstd_g * gamma + beta ), group statistics from ur_chan_stats. */
+/* out = [silu]( (cat(x1,x2) - mean_g) * rstd_g * gamma + beta ), group statistics from ur_chan_stats (or from the
+ * ur_conv_gemm epilogue).  stats2 == NULL: stats is [batch][c1+c2][2]; else stats is [batch][c1][2] and stats2 is
+ * [batch][c2][2] (each source carries the statistics its producer accumulated). */
 int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2, int64_t is2, int c2,
-                  const double* stats, int groups, int batch, int pixels, const float* gamma, const float* beta,
+                  const double* stats, const double* stats2, int groups, int batch, int pixels, const float* gamma, const float* beta,
                   float eps, int silu, void* out, int64_t ldo, int64_t iso, void* stream);
 /* One-launch nn.GroupNorm (+SiLU) over cat(x1, x2): a thread-block cluster per image keeps the partial statistics in
  * distributed shared memory, so there is no statistics array and no second launch (ur_groupnorm_cluster.cu).  Same

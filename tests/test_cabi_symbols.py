@@ -42,7 +42,7 @@ def test_conv_desc_matches_header_field_order():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|int64_t|int)\s*\*?", "", decl).strip()
+        decl = re.sub(r"^(const\s+)?(void|float|double|int64_t|int)\s*\*?", "", decl).strip()
         names += [re.sub(r"\[\d+\]|[\*\s]", "", n) for n in decl.split(",")]
     assert names == [f[0] for f in ConvDesc._fields_]
 

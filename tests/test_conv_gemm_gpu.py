@@ -238,3 +238,44 @@ def test_conv3x3_split_k(B, H, W, Cin, Cout):
     finally:
         _cabi.lib().ur_debug_set_gemm_splitk(old)
     assert_close(y, y0, 2e-3, "split-K vs unsplit")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(2, 16, 16, 64, 320, 9), (1, 24, 40, 128, 320, 9), (3, 8, 8, 320, 640, 9),
+                                                 (8, 8, 8, 1280, 1280, 9), (2, 64, 64, 320, 320, 1),
+                                                 (5, 4, 4, 256, 200, 9), (1, 20, 136, 64, 128, 9)])
+def test_epilogue_group_norm_statistics(B, H, W, Cin, Cout, taps):
+    """want_stats: the (sum, sumsq) per (image, channel) accumulated by the GEMM epilogue (or its fall-backs for tiles
+    spanning images / split-K) equal a ur_chan_stats pass over the finished output."""
+    from unirestore_b200 import ops
+    x = _rand(B, Cin, H, W, seed=110)
+    k = 3 if taps == 9 else 1
+    w = _rand(Cout, Cin, k, k, seed=111, scale=(taps * Cin) ** -0.5)
+    b = _rand(Cout, seed=112)
+    r = _rand(B, H, W, Cout, seed=113).to(torch.bfloat16)
+    xb, wb = _nhwc(x), w.to(torch.bfloat16)
+    y = ops.conv_gemm(xb, ops.pack_conv_weight(wb), Cout, taps=ops.TAPS_3x3 if taps == 9 else ops.TAPS_1x1, bias=b,
+                      residual=r, want_stats=True)
+    got = y._ur_stats
+    ref = ops.chan_stats(y)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (B, Cout, 2)
+    scale = ref.abs().amax(dim=(0, 1), keepdim=True).clamp_min(1e-6)
+    err = ((got - ref).abs() / scale).max().item()
+    assert err < 1e-4, "epilogue statistics differ from ur_chan_stats: %.3e" % err
+
+
+def test_group_norm_uses_epilogue_statistics():
+    """group_norm on a tensor that carries epilogue statistics (one or both concat sources) == the two-pass result."""
+    from unirestore_b200 import ops
+    B, H, W, C = 2, 16, 16, 320
+    xb = _nhwc(_rand(B, 64, H, W, seed=120))
+    w = _rand(C, 64, 3, 3, seed=121, scale=(9 * 64) ** -0.5).to(torch.bfloat16)
+    g, be = _rand(2 * C, seed=122), _rand(2 * C, seed=123)
+    y1 = ops.conv_gemm(xb, ops.pack_conv_weight(w), C, taps=ops.TAPS_3x3, want_stats=True)
+    y2 = ops.conv_gemm(xb, ops.pack_conv_weight(w), C, taps=ops.TAPS_3x3)          # no statistics attached
+    a = ops.group_norm(y1, 32, g[:C].contiguous(), be[:C].contiguous(), 1e-5, silu=True)
+    bq = ops.group_norm(y2, 32, g[:C].contiguous(), be[:C].contiguous(), 1e-5, silu=True)
+    assert_close(a, bq, 2e-3, "group_norm with epilogue statistics")
+    c1 = ops.group_norm(y1, 32, g, be, 1e-5, x2=y2)
+    c2 = ops.group_norm(y2, 32, g, be, 1e-5, x2=y2)
+    assert_close(c1, c2, 2e-3, "concat group_norm with mixed statistics sources")

@@ -37,6 +37,7 @@ class ConvDesc(C.Structure):
         ("chscale", C.c_void_p), ("chscale_sb", C.c_int64),
         ("residual", C.c_void_p), ("res_sb", C.c_int64), ("res_sy", C.c_int64), ("res_sx", C.c_int64),
         ("act", C.c_int), ("bn", C.c_int),
+        ("stats", C.c_void_p), ("stats_ld", C.c_int), ("stats_off", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
@@ -60,7 +61,7 @@ SIGNATURES = {
     "ur_group_norm": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _I, _I, _I, _P, _P, _F, _I, _P, _I64, _I64, _P]),
     "ur_group_norm_cluster_size": (C.c_int, []),
     "ur_debug_set_group_norm_cluster": (C.c_int, [C.c_int]),
-    "ur_norm_apply": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _P, _I, _I, _I, _P, _P, _F, _I, _P, _I64,
+    "ur_norm_apply": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _P, _P, _I, _I, _I, _P, _P, _F, _I, _P, _I64,
                                 _I64, _P]),
     "ur_layernorm": (C.c_int, [_P, _I64, _P, _I64, _I64, _I, _P, _P, _F, _P]),
     "ur_scale_channels": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _P]),

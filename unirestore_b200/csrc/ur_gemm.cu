@@ -356,6 +356,14 @@ static void pick_tile_config(int n, long long m_tiles, int nkb, int fixed_bn, bo
   *pair_out = best_pair;
 }
 
+// statistics of the finished bf16 output through the stand-alone kernel (tiles spanning images, split-K)
+static int stats_fallback(const ur_conv_desc* d, int n_out, cudaStream_t stream) {
+  if (d->out_sy != static_cast<int64_t>(d->wout) * d->out_sx && d->hout > 1)
+    return set_error(UR_ERR_ARG, "ur_conv_gemm: stats fallback needs a dense pixel pitch");
+  return ur_chan_stats(d->out, d->out_sx, d->out_sb, d->batch, d->hout * d->wout, n_out, d->stats, d->stats_ld,
+                       d->stats_off, 0, stream);
+}
+
 extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!d || !d->x1 || !d->w || !d->out) return set_error(UR_ERR_ARG, "ur_conv_gemm: null pointer");
@@ -460,6 +468,8 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   p.ksplit = 1;
   p.ws = nullptr;
   p.tma_store = 0;
+  p.stats = nullptr;
+  p.stats_ld = 0;
 
   // ---- fast path (persistent kernel): bf16 output with 16-byte aligned pitches
   const int n_out = gated ? d->n / 2 : d->n;
@@ -523,6 +533,13 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
       const bool str_ok = d->out_sx > 0 && (d->hout == 1 || d->out_sy > 0) && (d->batch == 1 || d->out_sb > 0);
       if (str_ok && encode_tensor_map(&mO, d->out, 4, dims, str, box, es, 64) == UR_OK) p.tma_store = 1;
     }
+    // GroupNorm statistics of the output: fused into the epilogue when an M tile never spans two images and K is not
+    // split; otherwise a ur_chan_stats pass over the finished output (dense pixel pitch required) does the same
+    const bool stats_fused = d->stats && Bt == 1 && !split_ok;
+    if (stats_fused) {
+      p.stats = d->stats + 2LL * d->stats_off;
+      p.stats_ld = d->stats_ld;
+    }
     const int n_tiles = (d->n + bn - 1) / bn;
     const long long m_tiles = static_cast<long long>(p.tiles_x) * p.tiles_y * tiles_b;
     const long long total = static_cast<long long>(n_tiles) * (pair_path ? (m_tiles + 1) / 2 : m_tiles);
@@ -545,12 +562,17 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
         if (e != cudaSuccess) return set_cuda_error(e, "ur_conv_gemm split-K memset");
         int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total * s), n_tiles, stream);
         if (rc) return rc;
-        return launch_splitk_finish(p, stream);
+        rc = launch_splitk_finish(p, stream);
+        if (rc || !d->stats) return rc;
+        return stats_fallback(d, n_out, stream);
       }
     }
-    return launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total), n_tiles, stream);
+    int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total), n_tiles, stream);
+    if (rc || !d->stats || stats_fused) return rc;
+    return stats_fallback(d, n_out, stream);
   }
 
+  if (d->stats) return set_error(UR_ERR_ARG, "ur_conv_gemm: stats needs the bf16 fast path");
   dim3 grid((d->n + bn - 1) / bn, p.tiles_x * p.tiles_y * tiles_b, 1);
   if (grid.y > 65535) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many M tiles");
   switch (bn) {

@@ -55,6 +55,8 @@ struct GemmParams {
   const bf16* residual;
   long long res_sb, res_sy, res_sx;
   int act;
+  double* stats;      // persistent kernel: (sum, sumsq) of the bf16 output per (image, channel) accumulated here (GroupNorm
+  int stats_ld;       //   statistics fused into the epilogue); channel n of image b at stats[(b * stats_ld + n) * 2]
   int tma_store;      // persistent kernel: 1 = epilogue sub-blocks leave through TMA stores (mapOut), 0 = coalesced st.global
   int ksplit;         // split-K factor (1 = off); work unit u -> (tile u / ksplit, K slice u % ksplit)
   float* ws;          // split-K: dense fp32 [B*Ho*Wo, N] partial sums (red.global.add), epilogue deferred to splitk_finish

@@ -37,7 +37,7 @@ struct PCfg {
   static constexpr int kWRows = PAIR ? BN / 2 : BN;
   static constexpr int kWBytes = kWRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kFixed = 2 * kEpiStageBytes + 4 * BN * 4 + 512;
+  static constexpr int kFixed = 2 * kEpiStageBytes + 4 * BN * 4 + 2 * 128 * 8 + 512;
   static constexpr int kFit = (227 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
@@ -79,7 +79,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   uint8_t* staging = smem + STAGES * kStageBytes;                          // [2 groups][128 x 80 B]
   float* s_add = reinterpret_cast<float*>(staging + 2 * kEpiStageBytes);    // [2][BN]
   float* s_mul = s_add + 2 * BN;                                            // [2][BN]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_mul + 2 * BN);
+  float* s_stat = s_mul + 2 * BN;                                           // [2 groups][128] float2 (epilogue statistics)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + 2 * 128 * 2);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -500,6 +501,50 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
                 for (int k = 0; k < 8; ++k)
                   if (nout0 + col + k < n_out) outp[ooff(i) + col + k] = sv[k];
               }
+            }
+          }
+        }
+        if (p.stats) {
+          // ---- fused GroupNorm statistics: column sums / sums of squares of the bf16 tile just staged.  Thread gt
+          //      takes column (gt & 31) over rows 32 * (gt >> 5) .. + 31 (one conflict-free 2-byte LDS per row; the
+          //      swizzle only depends on (row >> 1) & 3, so four base pointers cover all rows); the four row quarters
+          //      meet in shared memory and one warp adds them to the fp64 statistics of image tc.b0 (M tiles never
+          //      span images here: Bt == 1)
+          const int scol = gt & 31, sq4 = gt >> 5;
+          const uint8_t* sb0 = stg + sq4 * 32 * 64 + (scol & 7) * 2;
+          const int ch = scol >> 3;
+          const uint8_t* sbk[4] = {sb0 + ((ch ^ 0) << 4), sb0 + ((ch ^ 1) << 4), sb0 + ((ch ^ 2) << 4), sb0 + ((ch ^ 3) << 4)};
+          float s1 = 0.f, s2 = 0.f;
+          const bool tile_inside = tc.x0 + Wt <= p.Wo && tc.y0 + Ht <= p.Ho;
+          if (tile_inside) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float v = __uint_as_float(
+                  static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(sbk[(i >> 1) & 3] + i * 64)) << 16);
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          } else {
+            for (int i = 0; i < 32; ++i) {
+              const int rr = sq4 * 32 + i;
+              const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
+              float v = __uint_as_float(
+                  static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(sbk[(i >> 1) & 3] + i * 64)) << 16);
+              if (x >= p.Wo || y >= p.Ho) v = 0.f;
+              s1 += v;
+              s2 = fmaf(v, v, s2);
+            }
+          }
+          float2* sred = reinterpret_cast<float2*>(s_stat) + grp * 128;
+          sred[gt] = make_float2(s1, s2);
+          group_barrier(8 + grp);
+          if (gt < 32) {
+            const float2 a0 = sred[gt], a1 = sred[gt + 32], a2 = sred[gt + 64], a3 = sred[gt + 96];
+            const int ncol = nout0 + c + gt;
+            if (ncol < n_out && tc.b0 < p.B) {
+              double* sp = p.stats + (static_cast<long long>(tc.b0) * p.stats_ld + ncol) * 2;
+              atomicAdd(sp, static_cast<double>((a0.x + a1.x) + (a2.x + a3.x)));
+              atomicAdd(sp + 1, static_cast<double>((a0.y + a1.y) + (a2.y + a3.y)));
             }
           }
         }

@@ -65,7 +65,8 @@ __global__ void chan_stats_kernel(const bf16* __restrict__ x, long long ld, long
 // ------------------------------------------------------------------------------------ norm_apply
 __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, long long is1, int C1,
                                   const bf16* __restrict__ x2, long long ld2, long long is2, int C2,
-                                  const double* __restrict__ stats, int G, int P, int CV, int PL, int chunk,
+                                  const double* __restrict__ stats, const double* __restrict__ stats2, int G, int P,
+                                  int CV, int PL, int chunk,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                   bf16* __restrict__ out, long long ldo, long long iso) {
   pdl_launch_dependents();
@@ -74,11 +75,14 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
   const int C = C1 + C2;
   const int cg = C / G;
   const int b = blockIdx.y;
-  const double* st = stats + static_cast<long long>(b) * C * 2;
+  // statistics of channel c: one array over cat(x1, x2), or one array per source
+  const double* st1 = stats + static_cast<long long>(b) * (stats2 ? C1 : C) * 2;
+  const double* st2 = stats2 ? stats2 + static_cast<long long>(b) * C2 * 2 - 2 * C1 : st1;
   const double inv_n = 1.0 / (static_cast<double>(P) * cg);
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double s = 0.0, q = 0.0;
     for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      const double* st = c < C1 ? st1 : st2;
       s += st[2 * c];
       q += st[2 * c + 1];
     }
@@ -285,7 +289,8 @@ extern "C" int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int 
 }
 
 extern "C" int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2,
-                             int64_t is2, int c2, const double* stats, int groups, int batch, int pixels,
+                             int64_t is2, int c2, const double* stats, const double* stats2, int groups, int batch,
+                             int pixels,
                              const float* gamma, const float* beta, float eps, int silu, void* out, int64_t ldo,
                              int64_t iso, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -297,7 +302,7 @@ extern "C" int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, c
   pick_block(C, pixels, CV, PL, chunk, nchunks, batch);
   dim3 grid(nchunks, batch);
   launch_kernel(norm_apply_kernel, dim3(grid), dim3(CV * PL), 2 * groups * sizeof(float), stream, 
-      static_cast<const bf16*>(x1), ld1, is1, c1, static_cast<const bf16*>(x2), ld2, is2, c2, stats, groups, pixels, CV,
+      static_cast<const bf16*>(x1), ld1, is1, c1, static_cast<const bf16*>(x2), ld2, is2, c2, stats, stats2, groups, pixels, CV,
       PL, chunk, gamma, beta, eps, silu, static_cast<bf16*>(out), ldo, iso);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "ur_norm_apply launch");

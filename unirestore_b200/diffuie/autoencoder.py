@@ -63,7 +63,7 @@ class SkipConnectedAutoEncoder(nn.Module):
         """images fp32 [B,3,H,W] in [0,1] -> (z fp32 [B,4,h,w], z8 bf16 [B,h,w,8], skips bf16 NHWC)."""
         enc, pk = self.vae.encoder, self.vae.encoder.pk
         x = ops.image_to_nhwc8(images.float(), 2.0, -1.0)                                    # autoencoder.py:151
-        x = ops.conv_gemm(x, pk["w_in"], enc.conv_in.out_channels, taps=ops.TAPS_3x3, bias=pk["b_in"])
+        x = ops.conv_gemm(x, pk["w_in"], enc.conv_in.out_channels, taps=ops.TAPS_3x3, bias=pk["b_in"], want_stats=True)
         skips = []
         for i, blk in enumerate(enc.down_blocks[:-1]):                                       # autoencoder.py:18-24
             # the reference saves the skip AFTER the down-sampler of block i (block output), CFRM applied first
@@ -93,7 +93,7 @@ class SkipConnectedAutoEncoder(nn.Module):
         _, z8 = ops.latent_axpby(latents.float().contiguous(), 1.0, want_out=False, want_nhwc8=True,
                                  scale8=1.0 / float(self.vae.config["scaling_factor"]))          # autoencoder.py:170
         z8 = ops.conv_gemm(z8, vp["wpq"], 8, bias=vp["bpq"])
-        x = ops.conv_gemm(z8, pk["w_in"], dec.conv_in.out_channels, taps=ops.TAPS_3x3, bias=pk["b_in"])
+        x = ops.conv_gemm(z8, pk["w_in"], dec.conv_in.out_channels, taps=ops.TAPS_3x3, bias=pk["b_in"], want_stats=True)
         x = dec.mid_block.run(x)
         B = x.shape[0]
         cond = prompt.detach().float().unsqueeze(0).expand(B, -1, -1).contiguous() if prompt is not None else None

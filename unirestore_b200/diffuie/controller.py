@@ -58,7 +58,8 @@ class Controller(UrModule):
 
     def run(self, z8, emb):
         """z8: bf16 [B,h,w,8] (latent padded to 8 channels); emb fp32 [1 or B, 4*model_channels]."""
-        h = ops.conv_gemm(z8, self.pk["w_in"], self.model_channels, taps=ops.TAPS_3x3, bias=self.pk["b_in"])
+        h = ops.conv_gemm(z8, self.pk["w_in"], self.model_channels, taps=ops.TAPS_3x3, bias=self.pk["b_in"],
+                          want_stats=True)
         taps = []
         for blk in self.down_blocks:
             h, outs = blk.run(h, emb)

@@ -32,7 +32,7 @@ class CSCEAdapter(UrModule):
         p = self.pk
         s = ops.conv_gemm(condition, p["wp"], self.c_in, bias=p["bp"], residual=x)
         h = ops.conv_gemm(s, p["w0"], self.c_emb, bias=p["b0"], act=ops.UR_ACT_GELU)
-        return ops.conv_gemm(h, p["w2"], self.c_in, bias=p["b2"], residual=s)
+        return ops.conv_gemm(h, p["w2"], self.c_in, bias=p["b2"], residual=s, want_stats=True)   # skip -> up-block GroupNorm
 
     def forward(self, x, condition):
         return to_nchw(self.run(to_nhwc(x), to_nhwc(condition)), x.dtype)

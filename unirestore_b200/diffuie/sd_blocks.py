@@ -54,6 +54,15 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+def _view_keep_stats(t, shape):
+    """``t.view(shape)`` that keeps the epilogue-accumulated GroupNorm statistics attached (views drop attributes)."""
+    v = t.view(shape)
+    st = getattr(t, "_ur_stats", None)
+    if st is not None:
+        v._ur_stats = st
+    return v
+
+
 def pack_conv(conv: nn.Conv2d | nn.Linear, pad_cin: int | None = None, pad_cout: int | None = None):
     """-> (bf16 [Cout', taps*Cin'], fp32 bias [Cout']) with optional zero padding of Cin / Cout."""
     w = conv.weight.detach().float()
@@ -142,13 +151,14 @@ class ResnetBlock2D(UrModule):
                     cache.clear()
                 hit = cache[id(temb)] = (temb, ops.small_linear(temb, p["wt"], p["tb"], act_in="silu"))
             tvec = hit[1]
-        h = ops.conv_gemm(h, p["w1"], co, taps=TAPS_3x3, bias=p["c1b"], rowvec=tvec)
+        # want_stats: the GEMM epilogue accumulates the statistics of the GroupNorm that consumes its output
+        h = ops.conv_gemm(h, p["w1"], co, taps=TAPS_3x3, bias=p["c1b"], rowvec=tvec, want_stats=True)
         h = ops.group_norm(h, self.groups, p["g2"], p["b2"], self.eps, silu=True)
         if self.conv_shortcut is not None:
             res = ops.conv_gemm(x, p["ws"], co, x2=x2, bias=p["sb"])
         else:
             res = x
-        return ops.conv_gemm(h, p["w2"], co, taps=TAPS_3x3, bias=p["c2b"], residual=res)
+        return ops.conv_gemm(h, p["w2"], co, taps=TAPS_3x3, bias=p["c2b"], residual=res, want_stats=True)
 
 
 class Downsample2D(UrModule):
@@ -170,7 +180,7 @@ class Downsample2D(UrModule):
         else:
             ho, wo, taps = (H - 2) // 2 + 1, (W - 2) // 2 + 1, TAPS_3x3_NOPAD
         return ops.conv_gemm(x, self.pk["w"], self.out_channels, taps=taps, stride=2, hout=ho, wout=wo,
-                             bias=self.pk["b"])
+                             bias=self.pk["b"], want_stats=True)
 
 
 class Upsample2D(UrModule):
@@ -257,7 +267,7 @@ class Attention(UrModule):
         kv = self._ctx_kv
         return kv[..., : self.inner], kv[..., self.inner:]
 
-    def run_tokens(self, x, ctx=None, residual=None):
+    def run_tokens(self, x, ctx=None, residual=None, want_stats=False):
         """x bf16 [B,T,C] -> to_out(attn(x[, ctx])) (+ residual)."""
         p, C = self.pk, self.inner
         if self.is_cross:
@@ -267,7 +277,7 @@ class Attention(UrModule):
             qkv = ops.conv_gemm(x, p["wqkv"], 3 * C, bias=p["bqkv"])
             q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         a = ops.attention(q, k, v, self.heads)
-        return ops.conv_gemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual)
+        return ops.conv_gemm(a, p["wo"], self.query_dim, bias=p["bo"], residual=residual, want_stats=want_stats)
 
     def run(self, x):
         """Spatial self-attention block on bf16 NHWC: GN -> qkv -> SDPA -> to_out -> + x."""
@@ -275,7 +285,8 @@ class Attention(UrModule):
         B, H, W, C = x.shape
         xn = ops.group_norm(x, self.groups, p["gn_g"], p["gn_b"], self.eps) if self.group_norm is not None else x
         res = x.view(B, H * W, C) if self.residual_connection else None
-        return self.run_tokens(xn.view(B, H * W, C), residual=res).view(B, H, W, C)
+        y = self.run_tokens(xn.view(B, H * W, C), residual=res, want_stats=True)
+        return _view_keep_stats(y, (B, H, W, C))
 
 
 class GEGLU(nn.Module):
@@ -355,7 +366,8 @@ class Transformer2DModel(UrModule):
         t = ops.conv_gemm(t.view(B, H * W, C), p["wi"], self.inner, bias=p["bi"])
         for blk in self.transformer_blocks:
             t = blk.run(t, ctx)
-        return ops.conv_gemm(t, p["wo"], C, bias=p["bo"], residual=x.view(B, H * W, C)).view(B, H, W, C)
+        y = ops.conv_gemm(t, p["wo"], C, bias=p["bo"], residual=x.view(B, H * W, C), want_stats=True)
+        return _view_keep_stats(y, (B, H, W, C))
 
 
 # ------------------------------------------------------------------------------------------------- UNet blocks
@@ -558,7 +570,8 @@ class UNet2DConditionModel(UrModule):
         return p
 
     def run_conv_in(self, z8):
-        return ops.conv_gemm(z8, self.pk["w_in"], self.conv_in.out_channels, taps=TAPS_3x3, bias=self.pk["b_in"])
+        return ops.conv_gemm(z8, self.pk["w_in"], self.conv_in.out_channels, taps=TAPS_3x3, bias=self.pk["b_in"],
+                             want_stats=True)
 
     def run_head(self, x):
         """GN -> SiLU -> conv_out; returns fp32 channels-last [B,h,w,8] (channels >= out_channels are zero)."""

@@ -52,6 +52,7 @@ def _check_nhwc(t, name):
     return ld
 
 
+_ABLATE = set(filter(None, os.environ.get("UR_ABLATE", "").split(",")))   # development: time-share ablations
 _WS = {}
 _ROLE = ["main"]      # which execution context issues the calls: "main" or "ctl" (the Controller's side stream)
 
@@ -68,11 +69,14 @@ def _workspace(device, nbytes=16 << 20):
 
 def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None, bias=None, rowvec=None,
               chscale=None, residual=None, act=UR_ACT_NONE, alpha=1.0, out=None, out_dtype=torch.bfloat16,
-              group_kc=0, group_nc=0, w_batched=False, bn=0):
+              group_kc=0, group_nc=0, w_batched=False, bn=0, want_stats=False, stats=None):
     """``out = epilogue(alpha * conv(x [cat x2], w))`` -- see ``ur_conv_gemm`` in include/unirestore_b200.h.
 
     ``w`` is the packed bf16 weight ``[n, ntaps * kc]`` (``[batch, n, k]`` when ``w_batched``).
     ``out`` may be a strided NHWC view (channel slice, or ``full[:, py::2, px::2]`` for sub-pixel phases).
+    ``want_stats``: the per-(image, channel) (sum, sumsq) of the bf16 output -- the statistics pass of the GroupNorm
+    that consumes it -- are accumulated by the GEMM epilogue and attached to the result as ``._ur_stats``
+    (``stats``: accumulate into this existing ``[B, n_out, 2]`` fp64 buffer instead, e.g. the 4 sub-pixel phases).
     """
     squeeze = x.dim()
     x = _as4(x)
@@ -137,6 +141,11 @@ def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None
         d.residual = r.data_ptr()
         d.res_sb, d.res_sy, d.res_sx = r.stride(0), r.stride(1), r.stride(2)
     d.act, d.bn = act, bn
+    if (want_stats or stats is not None) and out.dtype == torch.bfloat16 and "nofusedstats" not in _ABLATE:
+        if stats is None:
+            stats = new_stats(x.device, B, n_out)
+        d.stats, d.stats_ld, d.stats_off = stats.data_ptr(), n_out, 0
+        ret._ur_stats = stats
     ws = _workspace(x.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     _cabi.ensure_init(x.device.index or 0)
@@ -225,6 +234,18 @@ def stats_arena_end(device):
     _ROLE[0] = "main"
 
 
+def new_stats(device, B, channels):
+    """Zeroed fp64 ``[B, channels, 2]`` statistics buffer: from the per-step pool when one is active, else a fresh fill."""
+    a, n = _arena_for(device), B * channels * 2
+    if a.active:
+        if a.off + n <= (a.hwm if a.hwm else a.buf.numel()):
+            st = a.buf[a.off:a.off + n].view(B, channels, 2)
+            a.off += n
+            return st
+        a.off += n              # grows the high-water mark for the next pass
+    return torch.zeros((B, channels, 2), device=device, dtype=torch.float64)
+
+
 def chan_stats(x, stats=None, offset=0, total_channels=None, zero=True):
     """fp64 (sum, sumsq) per (image, channel) -> ``[B, total_channels, 2]``."""
     B, P, Cc, ld, ist = _geom(x)
@@ -244,8 +265,9 @@ def chan_stats(x, stats=None, offset=0, total_channels=None, zero=True):
     return stats
 
 
-def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None):
-    """GroupNorm / InstanceNorm apply on ``cat(x, x2)`` (channel dim); returns a dense bf16 tensor."""
+def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None, stats2=None):
+    """GroupNorm / InstanceNorm apply on ``cat(x, x2)`` (channel dim); returns a dense bf16 tensor.
+    ``stats2`` given: ``stats`` covers the channels of ``x`` and ``stats2`` those of ``x2``."""
     B, P, C1, ld1, is1 = _geom(x)
     C2, ld2, is2 = 0, 0, 0
     if x2 is not None:
@@ -255,7 +277,7 @@ def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None
     if out is None:
         out = torch.empty(tuple(x.shape[:-1]) + (C1 + C2,), device=x.device, dtype=torch.bfloat16)
     _, _, Co, ldo, iso = _geom(out)
-    check(_lib().ur_norm_apply(_ptr(x), ld1, is1, C1, _ptr(x2), ld2, is2, C2, _ptr(stats), groups, B, P,
+    check(_lib().ur_norm_apply(_ptr(x), ld1, is1, C1, _ptr(x2), ld2, is2, C2, _ptr(stats), _ptr(stats2), groups, B, P,
                                _f32(gamma, "gamma"), _f32(beta, "beta"), eps, int(silu), _ptr(out), ldo, iso,
                                _stream()), "ur_norm_apply")
     return out
@@ -266,9 +288,6 @@ def norm_apply(x, stats, groups, gamma, beta, eps, silu=False, x2=None, out=None
 # ur_norm_apply on every per-step shape (16-CTA clusters are co-scheduled too sparsely and lose more), so it is off
 # by default; set UNIRESTORE_FUSED_GN_MB to route tensors up to that many MiB through it.
 FUSED_GN_MAX_BYTES = int(os.environ.get("UNIRESTORE_FUSED_GN_MB", "0")) << 20
-
-
-_ABLATE = set(filter(None, os.environ.get("UR_ABLATE", "").split(",")))   # development: time-share ablations (WRONG results)
 
 
 def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
@@ -295,10 +314,17 @@ def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
                                    _f32(beta, "beta"), eps, int(silu), _ptr(out), ldo, iso, _stream()),
               "ur_group_norm")
         return out
-    stats = chan_stats(x, total_channels=C1 + C2)
-    if x2 is not None:
+    # statistics: the ones the producing GEMM epilogue accumulated (``._ur_stats``) when present, else a pass here
+    st1 = getattr(x, "_ur_stats", None)
+    if x2 is None:
+        return norm_apply(x, st1 if st1 is not None else chan_stats(x), groups, gamma, beta, eps, silu)
+    st2 = getattr(x2, "_ur_stats", None)
+    if st1 is None and st2 is None:
+        stats = chan_stats(x, total_channels=C1 + C2)
         chan_stats(x2, stats=stats, offset=C1, total_channels=C1 + C2, zero=False)
-    return norm_apply(x, stats, groups, gamma, beta, eps, silu, x2)
+        return norm_apply(x, stats, groups, gamma, beta, eps, silu, x2)
+    return norm_apply(x, st1 if st1 is not None else chan_stats(x), groups, gamma, beta, eps, silu, x2,
+                      stats2=st2 if st2 is not None else chan_stats(x2))
 
 
 def layernorm(x, gamma, beta, eps):
