@@ -37,7 +37,7 @@ struct PCfg {
   static constexpr int kWRows = PAIR ? BN / 2 : BN;
   static constexpr int kWBytes = kWRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kFixed = 2 * kEpiStageBytes + 4 * BN * 4 + 2 * 128 * 8 + 512;
+  static constexpr int kFixed = 2 * kEpiStageBytes + 8 * BN * 4 + 2 * 128 * 8 + 512;
   static constexpr int kFit = (227 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
@@ -77,9 +77,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   constexpr uint32_t kTmemCols = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* staging = smem + STAGES * kStageBytes;                          // [2 groups][128 x 80 B]
-  float* s_add = reinterpret_cast<float*>(staging + 2 * kEpiStageBytes);    // [2][BN]
-  float* s_mul = s_add + 2 * BN;                                            // [2][BN]
-  float* s_stat = s_mul + 2 * BN;                                           // [2 groups][128] float2 (epilogue statistics)
+  float* s_add = reinterpret_cast<float*>(staging + 2 * kEpiStageBytes);    // [2 groups][2][BN] (a private copy per
+  float* s_mul = s_add + 4 * BN;                                            //  warp group: the groups never sync)
+  float* s_stat = s_mul + 4 * BN;                                           // [2 groups][128] float2 (epilogue statistics)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + 2 * 128 * 2);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
@@ -307,21 +307,26 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     int sbuf = 0;                                 // staging buffer of the next sub-block (alternates)
     const bool use_tma = p.tma_store != 0;
     bf16* outp = reinterpret_cast<bf16*>(p.out);
-    float a_nx = 0.f, m_nx = 1.f;                 // this thread's column of the NEXT tile's add / mul vectors
+    // this thread's two columns (gt, gt + 128) of the NEXT tile's add / mul vectors (every warp group stages its own copy)
+    float a_nx[2] = {0.f, 0.f}, m_nx[2] = {1.f, 1.f};
     auto fetch_vec = [&](int tt) {
       const TileCoord tn = tile_coord(p, fast_div(tt, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
-      const int n = tn.n0 + et;
       const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
       const int bb = tn.b0 < p.B ? tn.b0 : p.B - 1;      // (a PAIR ghost tile lies past the last image)
-      float a = 0.f;
-      if (n < p.N) {
-        if (p.bias) a += __ldg(p.bias + n);
-        if (p.rowvec) a += __ldg(p.rowvec + bb * p.rowvec_sb + n);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = gt + 128 * h;
+        const int n = tn.n0 + col;
+        float a = 0.f;
+        if (col < BN && n < p.N) {
+          if (p.bias) a += __ldg(p.bias + n);
+          if (p.rowvec) a += __ldg(p.rowvec + bb * p.rowvec_sb + n);
+        }
+        a_nx[h] = a;
+        m_nx[h] = (has_mul && col < ncols && no0 + col < n_out) ? __ldg(p.chscale + bb * p.chscale_sb + no0 + col) : 1.f;
       }
-      a_nx = a;
-      m_nx = (has_mul && et < ncols && no0 + et < n_out) ? __ldg(p.chscale + bb * p.chscale_sb + no0 + et) : 1.f;
     };
-    if (et < BN && u_first < total_tiles) fetch_vec(u_first);
+    if (u_first < total_tiles) fetch_vec(u_first);
     int it = 0;
     for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
       const TileCoord tc = tile_coord(p, fast_div(t, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
@@ -356,14 +361,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       }
       // ---- stage the per-column add / mul vectors of this tile (double-buffered by `as`); the values were
       //      fetched one tile ahead so their global-load latency hides behind the previous tile's epilogue
-      float* add = s_add + as * BN;
-      float* mul = s_mul + as * BN;
-      if (et < BN) {
-        add[et] = a_nx;
-        mul[et] = m_nx;
-        const int tn = t + u_stride;
-        if (tn < total_tiles) fetch_vec(tn);
+      float* add = s_add + (grp * 2 + as) * BN;
+      float* mul = s_mul + (grp * 2 + as) * BN;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (gt + 128 * h < BN) {
+          add[gt + 128 * h] = a_nx[h];
+          mul[gt + 128 * h] = m_nx[h];
+        }
       }
+      if (t + u_stride < total_tiles) fetch_vec(t + u_stride);
       // global element offsets of the 4 rows this thread moves in the cooperative phases (-1: outside the tensor)
       long long roff[4];
 #pragma unroll
@@ -382,7 +389,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       };
       // residual of this group's first sub-block, fetched (coalesced) while the main loop still runs
       uint4 rres[4];
-      int c = grp * 32;
+      int c = ((grp + it) & 1) * 32;            // the groups alternate which one takes the odd sub-block out (balance)
       if (p.residual) {
         const int col = c + cchunk * 8;
         const bool okc = c < ncols && nout0 + col + 8 <= n_out;
@@ -391,7 +398,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           rres[i] = (okc && roff[i] >= 0) ? __ldg(reinterpret_cast<const uint4*>(p.residual + roff[i] + col))
                                            : make_uint4(0u, 0u, 0u, 0u);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      group_barrier(10 + grp);                  // this group's add / mul copy is staged
       if (tracing && it < 8 && et == 0) p.trace[4 * 16 + it] = clock64();
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       if (tracing && it < 8 && et == 0) p.trace[5 * 16 + it] = clock64();

@@ -41,6 +41,8 @@ class DiffUIE(nn.Module):
         self._temb_cache = {}
         self._side_streams = {}
         self.overlap_controller = os.environ.get("UNIRESTORE_OVERLAP_CONTROLLER", "1") == "1"
+        self.split_unet = os.environ.get("UNIRESTORE_SPLIT_UNET", "0") == "1"
+        self._keep = []
         # CUDA-graph replay of the whole forward for static shapes (one capture per (shape, task, noise-mode));
         # every kernel behind the C-ABI is capture-safe (no allocation, no synchronisation).
         self.use_cuda_graph = os.environ.get("UNIRESTORE_CUDA_GRAPH", "0") == "1"
@@ -80,6 +82,13 @@ class DiffUIE(nn.Module):
             if hasattr(m, "invalidate"):
                 m.invalidate()
 
+    def _stream(self, name, device):
+        key = (name, device)
+        st = self._side_streams.get(key)
+        if st is None:
+            st = self._side_streams[key] = torch.cuda.Stream(device=device)
+        return st
+
     def _run_controller(self, z0_8, t: int):
         emb_c, _ = self._embeddings(t, z0_8.device)
         ops.stats_arena_begin(z0_8.device, "ctl")    # one fill instead of a memset node per GroupNorm
@@ -88,13 +97,30 @@ class DiffUIE(nn.Module):
         finally:
             ops.stats_arena_end(z0_8.device)
 
-    def _run_unet(self, zt8, control, t: int):
+    def _run_unet(self, zt8, control, t: int, role="main"):
         _, emb_u = self._embeddings(t, zt8.device)
-        ops.stats_arena_begin(zt8.device)
+        ops.stats_arena_begin(zt8.device, role)
         try:
             return self.base_model.run(zt8, control, emb_u)                      # unifie.py:149
         finally:
             ops.stats_arena_end(zt8.device)
+
+    def _run_unet_split(self, zt8, control, t: int, main):
+        """The UNet on two half batches, the second on its own stream: images are independent, and two chains of
+        small dependent kernels fill each other's idle SM time (tails, prologues, underfilled grids)."""
+        B = zt8.shape[0]
+        h = B // 2
+        s2 = self._stream("unet2", zt8.device)
+        s2.wait_stream(main)
+        with torch.cuda.stream(s2):
+            e2 = self._run_unet(zt8[h:], {k: v[h:] for k, v in control.items()}, t, role="unet2")
+        e1 = self._run_unet(zt8[:h], {k: v[:h] for k, v in control.items()}, t)
+        main.wait_stream(s2)
+        self._keep.append(e2)                      # produced on s2, consumed on main: kept alive until the loop ends
+        eps = torch.empty((B,) + tuple(e1.shape[1:]), device=e1.device, dtype=e1.dtype)
+        eps[:h].copy_(e1)
+        eps[h:].copy_(e2)
+        return eps
 
     def predict_eps(self, zt8, z0_8, t: int):
         return self._run_unet(zt8, self._run_controller(z0_8, t), t)
@@ -122,11 +148,10 @@ class DiffUIE(nn.Module):
         # grids).  Its outputs are kept alive until the loop ends, so no buffer crosses streams while being recycled.
         ts = [int(t) for t in self.scheduler.timesteps_host]
         main = torch.cuda.current_stream(z0.device)
-        side = self._side_streams.get(z0.device)
-        if side is None:
-            side = self._side_streams[z0.device] = torch.cuda.Stream(device=z0.device)
+        side = self._stream("ctl", z0.device)
         overlap = self.overlap_controller and len(ts) > 1
-        keep = []
+        split = self.split_unet and z0.shape[0] >= 2 and z0.shape[0] % 2 == 0
+        keep = self._keep = []
 
         def launch_controller(i):
             if not overlap:
@@ -147,10 +172,11 @@ class DiffUIE(nn.Module):
                 nxt = launch_controller(i + 1)
             if ev is not None:
                 main.wait_event(ev)
-            eps8 = self._run_unet(zt8, control, t)
+            eps8 = self._run_unet_split(zt8, control, t, main) if split else self._run_unet(zt8, control, t)
             zt8 = ops.ddim_step_(zt, eps8, self.scheduler.step_coefficients(t), bool(self.scheduler.config.clip_sample))
         if overlap:
             main.wait_stream(side)
+        self._keep = []
         return zt
 
     @torch.no_grad()
