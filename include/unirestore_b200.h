@@ -203,6 +203,13 @@ int ur_image_to_nhwc8(const float* img, int64_t sb, int64_t sc, int64_t sy, int6
 int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w, float a, float b,
                      float* out, void* stream);
 
+/* Image pre / post around the path (unifie.py:124-134,165-168): out = reflect_pad_{bottom,right}(bicubic_resize(img,
+ * (hr, wr))) on fp32 NCHW (arbitrary input strides in elements), F.interpolate(mode="bicubic", align_corners=False,
+ * antialias=False) + F.pad(mode="reflect") semantics; hr == hin && wr == win skips the resize.
+ * out: dense fp32 [batch, channels, hr + pad_b, wr + pad_r]. */
+int ur_resize_pad(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels, int hin,
+                  int win, int hr, int wr, int pad_b, int pad_r, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,3 +197,22 @@ def test_group_norm_cluster_kernel(B, H, W, C1, C2, G, silu):
         ops.chan_stats(x2, stats=st, offset=C1, total_channels=C1 + C2, zero=False)
     y2 = ops.norm_apply(x1, st, G, gamma, beta, 1e-5, silu, x2)
     assert_close(y, y2, 5e-3, "cluster vs two-launch group_norm")
+
+
+@pytest.mark.parametrize("B,H,W,size,pb,pr", [(2, 256, 256, (512, 512), 0, 0), (1, 300, 200, (768, 512), 0, 0),
+                                              (1, 512, 520, None, 0, 56), (1, 200, 333, (512, 853), 0, 43),
+                                              (2, 576, 640, (300, 333), 0, 0), (1, 515, 700, None, 61, 4)])
+def test_resize_pad_matches_torch(B, H, W, size, pb, pr):
+    """ur_resize_pad == F.pad(F.interpolate(bicubic, align_corners=False), reflect) (unifie.py:124-134,165-168)."""
+    import torch.nn.functional as F
+    from unirestore_b200 import ops
+    dev = torch.device("cuda:0")
+    x = torch.rand(B, 3, H, W, generator=torch.Generator().manual_seed(3)).to(dev)
+    ref = F.interpolate(x, size, mode="bicubic", align_corners=False, antialias=False) if size else x
+    if pb or pr:
+        ref = F.pad(ref, (0, pr, 0, pb), mode="reflect")
+    got = ops.resize_pad(x, size, pb, pr)
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 2e-5
+    xt = x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)          # non-contiguous (channels / strides) input
+    assert (ops.resize_pad(xt, size, pb, pr) - ref).abs().max().item() < 2e-5

@@ -75,3 +75,21 @@ def test_diffuie_forward_golden(model):
     y = model(img, g["task"], noise=(n_post.to(DEV), n_diff.to(DEV)))
     assert y.shape == g["out"].shape
     assert_close(y, g["out"].to(DEV), 1e-1, "DiffUIE.forward (2 DDIM steps, 512x640) vs reference golden")
+
+
+def test_diffuie_forward_small_input_vs_oracle(model):
+    """BASELINE configs[0]-style plumbing case: a small non-square LQ image goes through bicubic up-scaling to 512 on the
+    short side, reflect padding to a multiple of 64, the whole path, crop and bicubic resize back (unifie.py:124-134,
+    164-168) -- all on the GPU -- and is compared with the CPU oracle on identical weights and injected noise."""
+    from oracle import unirestore as O
+    from unirestore_b200.init_utils import deterministic_init_
+    torch.manual_seed(5)
+    img = torch.rand(1, 3, 200, 260)
+    # 200x260 -> 512x666 -> padded 512x704 -> latent 64x88
+    n_post, n_diff = torch.randn(1, 4, 64, 88), torch.randn(1, 4, 64, 88)
+    with torch.no_grad():
+        om = deterministic_init_(O.DiffUIE(*CFG)).eval()
+        ref = om(img, "seg", noise=(n_post, n_diff))
+    y = model(img.to(DEV), "seg", noise=(n_post.to(DEV), n_diff.to(DEV)))
+    assert y.shape == ref.shape == (1, 3, 200, 260)
+    assert_close(y, ref.to(DEV), 1e-1, "DiffUIE.forward (200x260 input: resize + reflect pad + crop + resize back) vs oracle")

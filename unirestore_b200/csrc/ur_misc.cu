@@ -397,6 +397,62 @@ __global__ void image_to_nhwc8_kernel(const float* __restrict__ img, long long s
         make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
   }
 }
+// ------------------------------------------------------------------------------------ image pre / post (8f rank 1)
+// F.interpolate(mode="bicubic", align_corners=False, antialias=False) followed by F.pad(mode="reflect") on the
+// right / bottom (unifie.py:124-134), and the resize back (unifie.py:165-168), on fp32 NCHW images in one gather:
+//   out[b,c,y,x] = bicubic(img, reflect_y(y), reflect_x(x))   for y < Hr + pad_b, x < Wr + pad_r
+// Same arithmetic as ATen's upsample_bicubic2d: src = (dst + 0.5) * (in / out) - 0.5, cubic convolution coefficients
+// with A = -0.75, taps clamped to the image.  Hr == Hin && Wr == Win: plain (reflect-padded) copy.
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.0f, x3 = 2.0f - t, u = 1.0f - t;
+  w[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+  w[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+  w[2] = ((A + 2.0f) * u - (A + 3.0f)) * u * u + 1.0f;
+  w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+__global__ void resize_pad_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy, long long sx,
+                                  int C, int Hin, int Win, int Hr, int Wr, int Ho, int Wo, float scale_y, float scale_x,
+                                  long long total, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const bool resize = Hr != Hin || Wr != Win;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int xx = static_cast<int>(i % Wo);
+    int yy = static_cast<int>((i / Wo) % Ho);
+    const int c = static_cast<int>((i / (static_cast<long long>(Wo) * Ho)) % C);
+    const long long b = i / (static_cast<long long>(Wo) * Ho * C);
+    if (xx >= Wr) xx = 2 * (Wr - 1) - xx;          // reflect (no edge repeat), pad < size guaranteed by the host
+    if (yy >= Hr) yy = 2 * (Hr - 1) - yy;
+    const float* src = img + b * sb + c * sc;
+    float v;
+    if (!resize) {
+      v = src[yy * sy + xx * sx];
+    } else {
+      const float fy = (yy + 0.5f) * scale_y - 0.5f, fx = (xx + 0.5f) * scale_x - 0.5f;
+      const float y0f = floorf(fy), x0f = floorf(fx);
+      const int y0 = static_cast<int>(y0f), x0 = static_cast<int>(x0f);
+      float wy[4], wx[4];
+      cubic_coeffs(fy - y0f, wy);
+      cubic_coeffs(fx - x0f, wx);
+      v = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ys = min(max(y0 - 1 + j, 0), Hin - 1);
+        float row = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int xs = min(max(x0 - 1 + k, 0), Win - 1);
+          row += wx[k] * src[ys * sy + xs * sx];
+        }
+        v += wy[j] * row;
+      }
+    }
+    out[i] = v;
+  }
+}
+
 // fp32 channels-last [B,Hs,Ws,ld] -> fp32 NCHW [B,C,H,W] = a*x + b over the top-left HxW crop (autoencoder.py:175,
 // unifie.py:164)
 __global__ void nhwc_to_image_kernel(const float* __restrict__ src, int ld, int Hs, int Ws, int C, int H, int W,
@@ -557,4 +613,17 @@ extern "C" int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int ba
   launch_kernel(nhwc_to_image_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, ld, hs, ws, channels, h, w, a,
                                                                                       b, total, out);
   UR_LAUNCH_CHECK("ur_nhwc_to_image");
+}
+
+extern "C" int ur_resize_pad(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels,
+                             int hin, int win, int hr, int wr, int pad_b, int pad_r, float* out, void* stream) {
+  if (!img || !out || batch <= 0 || channels <= 0 || hin <= 0 || win <= 0 || hr <= 0 || wr <= 0 || pad_b < 0 || pad_r < 0 ||
+      pad_b >= hr || pad_r >= wr)
+    return set_error(UR_ERR_ARG, "ur_resize_pad: bad arguments (reflect padding must be smaller than the image)");
+  const int ho = hr + pad_b, wo = wr + pad_r;
+  const long long total = static_cast<long long>(batch) * channels * ho * wo;
+  launch_kernel(resize_pad_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), img, sb, sc, sy,
+                sx, channels, hin, win, hr, wr, ho, wo, static_cast<float>(hin) / hr, static_cast<float>(win) / wr, total,
+                out);
+  UR_LAUNCH_CHECK("ur_resize_pad");
 }

@@ -198,18 +198,25 @@ class DiffUIE(nn.Module):
         org_h, org_w = images.shape[-2:]
         h, w = org_h, org_w
         images = images.float()
-        if h < 512 or w < 512:                                                   # unifie.py:124-129
+        resize = h < 512 or w < 512                                              # unifie.py:124-129
+        if resize:
             s = 512 / min(h, w)
             h, w = round(h * s), round(w * s)
-            images = F.interpolate(images, (h, w), mode="bicubic", align_corners=False, antialias=False)
-        if h % 64 or w % 64:                                                     # unifie.py:130-134
-            images = F.pad(images, (0, (64 - w % 64) % 64, 0, (64 - h % 64) % 64), mode="reflect")
+        pad_r, pad_b = (64 - w % 64) % 64, (64 - h % 64) % 64                     # unifie.py:130-134
+        if resize or pad_r or pad_b:
+            if images.is_cuda:      # bicubic resize + reflect pad in one kernel
+                images = ops.resize_pad(images, (h, w) if resize else None, pad_b, pad_r)
+            else:                   # (CPU tensors only reach the error paths of the ops below)
+                if resize:
+                    images = F.interpolate(images, (h, w), mode="bicubic", align_corners=False, antialias=False)
+                if pad_r or pad_b:
+                    images = F.pad(images, (0, pad_r, 0, pad_b), mode="reflect")
         n_post, n_diff = noise if noise is not None else (None, None)
         z0, z0_8, mids = self.ae.run_encode(images, enable_fr=self.fr_type is not None, noise=n_post)
         zt = self.restore_latents(z0, z0_8, n_diff) if self.control_type else z0
         preds = self.ae.run_decode(zt, mids, task, crop_hw=(h, w))               # unifie.py:155,164
         if (h, w) != (org_h, org_w):                                             # unifie.py:165-168
-            preds = F.interpolate(preds, (org_h, org_w), mode="bicubic", align_corners=False, antialias=False)
+            preds = ops.resize_pad(preds, (org_h, org_w))
         return preds
 
 

@@ -518,3 +518,16 @@ def nhwc_to_image(src, channels, h=None, w=None, a=1.0, b=0.0):
     check(_lib().ur_nhwc_to_image(_f32(src, "src"), ld, Hs, Ws, B, channels, h, w, a, b, _ptr(out), _stream()),
           "ur_nhwc_to_image")
     return out
+
+
+def resize_pad(img, size=None, pad_bottom=0, pad_right=0):
+    """``F.pad(F.interpolate(img, size, mode="bicubic", align_corners=False), (0, pad_right, 0, pad_bottom), "reflect")``
+    on a CUDA fp32 NCHW image in one kernel (unifie.py:124-134,165-168); ``size=None`` keeps the resolution."""
+    if img.dtype != torch.float32 or not img.is_cuda or img.dim() != 4:
+        raise ValueError("img must be a CUDA fp32 [B,C,H,W] tensor")
+    B, Cc, H, W = img.shape
+    hr, wr = (H, W) if size is None else (int(size[0]), int(size[1]))
+    out = torch.empty((B, Cc, hr + pad_bottom, wr + pad_right), device=img.device, dtype=torch.float32)
+    check(_lib().ur_resize_pad(_ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), B, Cc, H, W, hr, wr,
+                               pad_bottom, pad_right, _ptr(out), _stream()), "ur_resize_pad")
+    return out
