@@ -93,3 +93,20 @@ def test_diffuie_forward_small_input_vs_oracle(model):
     y = model(img.to(DEV), "seg", noise=(n_post.to(DEV), n_diff.to(DEV)))
     assert y.shape == ref.shape == (1, 3, 200, 260)
     assert_close(y, ref.to(DEV), 1e-1, "DiffUIE.forward (200x260 input: resize + reflect pad + crop + resize back) vs oracle")
+
+
+def test_predict_z0_per_sample_timesteps_vs_oracle(model):
+    """Training-time forward variant: per-sample timesteps -> per-image time-embedding row vectors
+    in the conv epilogues; compared with the CPU oracle's predict_z0 on a small latent."""
+    from oracle import unirestore as O
+    from unirestore_b200.init_utils import deterministic_init_
+    zt, z0 = rnd(31, 3, 4, 16, 16), rnd(32, 3, 4, 16, 16)
+    ts = torch.tensor([249, 999, 499])
+    with torch.no_grad():
+        om = deterministic_init_(O.DiffUIE(*CFG)).eval()
+        ref = om.predict_z0(zt, z0, ts)
+        same = om.predict_z0(zt, z0, torch.tensor([749, 749, 749]))
+    got = model.predict_z0(zt.to(DEV), z0.to(DEV), ts.to(DEV))
+    assert_close(got, ref.to(DEV), 5e-2, "predict_z0 with per-sample timesteps vs oracle")
+    got1 = model.predict_z0(zt.to(DEV), z0.to(DEV), torch.tensor([749], device=DEV))
+    assert_close(got1, same.to(DEV), 5e-2, "predict_z0 with one shared timestep vs oracle")

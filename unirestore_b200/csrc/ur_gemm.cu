@@ -572,13 +572,16 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     return stats_fallback(d, n_out, stream);
   }
 
-  if (d->stats) return set_error(UR_ERR_ARG, "ur_conv_gemm: stats needs the bf16 fast path");
+  if (d->stats && d->out_dtype != UR_DT_BF16) return set_error(UR_ERR_ARG, "ur_conv_gemm: stats needs a bf16 output");
   dim3 grid((d->n + bn - 1) / bn, p.tiles_x * p.tiles_y * tiles_b, 1);
   if (grid.y > 65535) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many M tiles");
+  int rc;
   switch (bn) {
-    case 64: return launch_conv_gemm<64, 4, 2>(p, mA1, mA2, mW, grid, stream);
-    case 128: return launch_conv_gemm<128, 3, 2>(p, mA1, mA2, mW, grid, stream);
-    case 160: return launch_conv_gemm<160, 3, 2>(p, mA1, mA2, mW, grid, stream);
-    default: return launch_conv_gemm<256, 4, 1>(p, mA1, mA2, mW, grid, stream);
+    case 64: rc = launch_conv_gemm<64, 4, 2>(p, mA1, mA2, mW, grid, stream); break;
+    case 128: rc = launch_conv_gemm<128, 3, 2>(p, mA1, mA2, mW, grid, stream); break;
+    case 160: rc = launch_conv_gemm<160, 3, 2>(p, mA1, mA2, mW, grid, stream); break;
+    default: rc = launch_conv_gemm<256, 4, 1>(p, mA1, mA2, mW, grid, stream); break;
   }
+  if (rc || !d->stats) return rc;
+  return stats_fallback(d, n_out, stream);          // non-persistent path: statistics by a pass over the output
 }

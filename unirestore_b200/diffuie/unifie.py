@@ -126,14 +126,28 @@ class DiffUIE(nn.Module):
         return self._run_unet(zt8, self._run_controller(z0_8, t), t)
 
     def predict_z0(self, latents, conditions, timesteps):                        # unifie.py:91-105
-        ts = sorted(set(int(t) for t in timesteps.reshape(-1).tolist()))
-        if len(ts) != 1:
-            raise NotImplementedError("predict_z0: one timestep per call on the CUDA path")
-        eps8 = self.predict_eps(ops.image_to_nhwc8(latents.float()), ops.image_to_nhwc8(conditions.float()), ts[0])
-        sa, sb = self.ddpm.noise_coefficients(ts[0])
+        """One-step estimate of z0 from noisy latents; ``timesteps`` int64 [1] or [B] (per-sample, as drawn by
+        ``diffuse`` during stage-2/3 training, engine_unifie.py:139-147)."""
+        tl = [int(t) for t in timesteps.reshape(-1).tolist()]
+        B = latents.shape[0]
+        if len(tl) not in (1, B):
+            raise ValueError("timesteps must have 1 or batch entries")
+        zt8, z0_8 = ops.image_to_nhwc8(latents.float()), ops.image_to_nhwc8(conditions.float())
         z = latents.float().clone()
-        # x0 = (x - sqrt(1-a) eps) / sqrt(a): the DDIM kernel with a_prev = 1 (sqrt(a_p) = 1, sqrt(1-a_p) = 0)
-        ops.ddim_step_(z, eps8, (sa, sb, 1.0, 0.0), want_nhwc8=False)
+        if len(set(tl)) == 1:
+            eps8 = self.predict_eps(zt8, z0_8, tl[0])
+            sa, sb = self.ddpm.noise_coefficients(tl[0])
+            # x0 = (x - sqrt(1-a) eps) / sqrt(a): the DDIM kernel with a_prev = 1 (sqrt(a_p) = 1, sqrt(1-a_p) = 0)
+            ops.ddim_step_(z, eps8, (sa, sb, 1.0, 0.0), want_nhwc8=False)
+            return z
+        # per-sample timesteps: [B, C] time embeddings -> per-image row vectors in the conv epilogues
+        ts = torch.tensor(tl, dtype=torch.int64, device=latents.device)
+        control = self.controller.run(z0_8, self.controller.time_embed(ts))
+        eps8 = self.base_model.run(zt8, control, self.base_model.time_embed(ts))
+        for i, t in enumerate(tl):
+            sa, sb = self.ddpm.noise_coefficients(t)
+            zi = z[i:i + 1]
+            ops.ddim_step_(zi, eps8[i:i + 1], (sa, sb, 1.0, 0.0), want_nhwc8=False)
         return z
 
     # ---------------------------------------------------------------------------------- inference (hot path)
