@@ -40,7 +40,8 @@ __device__ __forceinline__ T warp_uniform(T v) { return __shfl_sync(0xffffffffu,
 // Every kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization (ur_host.h launch_kernel): the
 // next kernel in the stream / graph may start while this one drains, runs its prologue (barrier init, TMEM
 // allocation, tensor-map prefetch, shared-memory setup) and then blocks in pdl_wait() until the predecessor has
-// completed and its writes are visible.  Rule: NO global-memory access before pdl_wait().
+// completed and its writes are visible.  Rule: before pdl_wait() a kernel touches NO memory a predecessor may write or
+// still read (activations, statistics, workspaces); weights / affine parameters are constant and may be prefetched.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
