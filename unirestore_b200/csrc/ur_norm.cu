@@ -257,8 +257,8 @@ static void pick_block(int C, int P, int& CV, int& PL, int& chunk, int& nchunks,
   CV = C / 8;
   PL = CV >= 256 ? 1 : 256 / CV;
   if (PL < 1) PL = 1;
-  // aim for ~4 waves of blocks over the GPU, at least 8 pixels per thread
-  static const int waves = getenv("UR_NORM_WAVES") ? atoi(getenv("UR_NORM_WAVES")) : 4;
+  // aim for ~8 waves of blocks over the GPU (same-box A/B in the full forward: 8 > 4 > 2), at least 8 pixels per thread
+  static const int waves = getenv("UR_NORM_WAVES") ? atoi(getenv("UR_NORM_WAVES")) : 8;
   const int target = max(1, (waves * num_sms()) / max(1, B));
   chunk = (P + target - 1) / target;
   const int min_chunk = PL * 8;
