@@ -210,6 +210,13 @@ int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int ch
 int ur_resize_pad(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels, int hin,
                   int win, int hr, int wr, int pad_b, int pad_r, float* out, void* stream);
 
+/* Metrics step right after the path (eval_image_restoration.py:71,255-313: 8-bit quantisation of the prediction,
+ * skimage peak_signal_noise_ratio / structural_similarity(win 7, uniform, sample covariance, channel_axis 0)):
+ * out[b] = { sum (t-p)^2 over the image, sum of the SSIM map over channels and the 3-pixel-cropped interior }, fp64.
+ * pred / target: dense fp32 [batch, channels, h, w] on the device. */
+int ur_image_metrics(const float* pred, const float* target, int batch, int channels, int h, int w, int quantize_pred,
+                     float data_range, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -216,3 +216,23 @@ def test_resize_pad_matches_torch(B, H, W, size, pb, pr):
     assert (got - ref).abs().max().item() < 2e-5
     xt = x.permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)          # non-contiguous (channels / strides) input
     assert (ops.resize_pad(xt, size, pb, pr) - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,quant", [(2, 64, 80, False), (1, 200, 333, True), (3, 7, 9, False)])
+def test_image_metrics_match_oracle(B, H, W, quant):
+    """ur_image_metrics (PSNR / SSIM sums) vs the numpy/scipy restatement of the skimage calls of the reference's
+    validate loop (eval_image_restoration.py:71,255-313)."""
+    import numpy as np
+    from oracle import metrics as OM
+    from unirestore_b200.metrics import SKPSNR, SKSSIM
+    g = torch.Generator().manual_seed(11)
+    tgt = torch.rand(B, 3, H, W, generator=g)
+    prd = (tgt + 0.05 * torch.randn(B, 3, H, W, generator=g)).clamp(0, 1)
+    ps, ss = SKPSNR(quantize=quant), SKSSIM(quantize=quant)
+    ps.update(prd.to("cuda:0"), tgt.to("cuda:0"))
+    ss.update(prd.to("cuda:0"), tgt.to("cuda:0"))
+    pn = OM.quantize8(prd.numpy()) if quant else prd.numpy()
+    ref_p = np.mean([OM.psnr(tgt[i].numpy(), pn[i]) for i in range(B)])
+    ref_s = np.mean([OM.ssim(pn[i], tgt[i].numpy()) for i in range(B)])
+    assert abs(ps.compute() - ref_p) < 1e-6 * abs(ref_p), (ps.compute(), ref_p)
+    assert abs(ss.compute() - ref_s) < 1e-8, (ss.compute(), ref_s)

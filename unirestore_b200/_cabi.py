@@ -78,6 +78,7 @@ SIGNATURES = {
     "ur_latent_axpby": (C.c_int, [_P, _F, _P, _F, _I, _I, _P, _P, _F, _P]),
     "ur_ddim_step": (C.c_int, [_P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P]),
     "ur_image_to_nhwc8": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "ur_image_metrics": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "ur_resize_pad": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "ur_nhwc_to_image": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P]),
 }
