@@ -117,3 +117,31 @@ def test_val_yaml_model_kwargs_drive_the_constructor():
     from unirestore_b200.diffuie import DiffUIE
     m = DiffUIE(**kw)
     assert m.scheduler.timesteps.tolist() == [999] and sorted(m.ae.vae.decoder.task_prompts.keys()) == ["cls", "ir", "seg"]
+
+
+def test_reference_checkpoint_surgery(model):
+    """engine_unifie.py:49-126: CFRM / Controller + SC-Tuner / TFA parameters restored by key prefix from Lightning
+    checkpoints; SD-Turbo backbone from diffusers-format state dicts."""
+    import torch
+    from unirestore_b200.checkpoint import load_reference_checkpoints, load_sd_turbo
+    full = {"model." + k: torch.full_like(v, 0.5) if v.is_floating_point() else v.clone()
+            for k, v in model.state_dict().items()}
+    ckpt = {"state_dict": full}
+    rep = load_reference_checkpoints(model, frenc=ckpt, cnet=ckpt, tedit=ckpt)
+    assert rep["cnet"]["model.controller."] > 100 and rep["cnet"]["model.base_model.csc_editors."] == 12 * 6
+    assert rep["frenc"]["model.ae.vae.encoder.fr_blocks."] > 100
+    assert float(model.controller.conv_in.weight.mean()) == 0.5
+    assert float(model.base_model.csc_editors[3].proj.bias.mean()) == 0.5
+    assert float(model.ae.vae.decoder.task_prompts["seg"].mean()) == 0.5
+    assert float(model.base_model.unet.conv_in.weight.mean()) != 0.5          # backbone untouched by the surgery
+    broken = {"state_dict": {k: v for k, v in full.items() if "controller.conv_in.bias" not in k}}
+    with pytest.raises(RuntimeError):
+        load_reference_checkpoints(model, cnet=broken)                         # strict, like the reference
+    unet_sd = {k: torch.zeros_like(v) for k, v in model.base_model.unet.state_dict().items()}
+    vae_sd = {k: torch.zeros_like(v) for k, v in model.ae.vae.state_dict().items()
+              if not k.startswith(("encoder.fr_blocks.", "decoder.task_prompts.", "decoder.task_editors."))}
+    load_sd_turbo(model, unet_sd, vae_sd)
+    assert float(model.base_model.unet.conv_in.weight.abs().max()) == 0.0
+    assert float(model.ae.vae.encoder.fr_blocks[0][0].conv1.weight.mean()) == 0.5   # CFRM kept
+    with pytest.raises(RuntimeError):
+        load_sd_turbo(model, None, {k: v for k, v in vae_sd.items() if k != "quant_conv.weight"})
