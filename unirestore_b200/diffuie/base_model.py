@@ -37,6 +37,8 @@ class ControlledUNet(UrModule):
         else:
             raise ValueError(f"control_type '{control_type}' not supported")
         self._ctx = None
+        self._sc_streams = {}
+        self.overlap_sc_tuner = os.environ.get("UNIRESTORE_OVERLAP_SCTUNER", "1") == "1"
 
     def _reset_cache(self):
         self._pk = None
@@ -67,13 +69,32 @@ class ControlledUNet(UrModule):
             if blk.downsamplers is not None:
                 x = blk.downsamplers[0].run(x)
                 skips.append(x)
+        # SC-Tuner (base_model.py:233-238) only touches the skips: the 12 adapters (36 small GEMMs) run on a side stream,
+        # deepest skip first (the order the decoder consumes them), under the mid block's 8x8 kernels that leave most
+        # SMs idle.  The decoder waits on one event per skip.
+        events = None
+        if self.overlap_sc_tuner and x.is_cuda:
+            main = torch.cuda.current_stream(x.device)
+            side = self._sc_streams.get(x.device)
+            if side is None:
+                side = self._sc_streams[x.device] = torch.cuda.Stream(device=x.device)
+            side.wait_stream(main)
+            events = [None] * len(skips)
+            with torch.cuda.stream(side):
+                for i in reversed(range(len(self.csc_editors))):
+                    skips[i] = self.csc_editors[i].run(skips[i], control[skips[i].shape[2]])
+                    events[i] = torch.cuda.Event()
+                    events[i].record(side)
         x = u.mid_block.resnets[0].run(x, emb)                             # base_model.py:153-160
         x = u.mid_block.resnets[1].run(u.mid_block.attentions[0].run(x, ctx), emb)
-        for i, ed in enumerate(self.csc_editors):                          # base_model.py:233-238
-            skips[i] = ed.run(skips[i], control[skips[i].shape[2]])
+        if events is None:
+            for i, ed in enumerate(self.csc_editors):                      # base_model.py:233-238
+                skips[i] = ed.run(skips[i], control[skips[i].shape[2]])
         for blk in u.up_blocks:                                            # base_model.py:173-203
             attns = blk.attentions if blk.has_cross_attention else [None] * len(blk.resnets)
             for r, a in zip(blk.resnets, attns):
+                if events is not None and events[len(skips) - 1] is not None:
+                    torch.cuda.current_stream(x.device).wait_event(events[len(skips) - 1])
                 x = r.run(x, emb, x2=skips.pop())
                 if a is not None:
                     x = a.run(x, ctx)
