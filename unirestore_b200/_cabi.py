@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libunirestore_b200.so")
+LIB_PATH = os.environ.get("UNIRESTORE_B200_LIB") or os.path.join(_HERE, "libunirestore_b200.so")   # (override: A/B of two builds)
 
 UR_ACT_NONE, UR_ACT_SILU, UR_ACT_GELU, UR_ACT_GEGLU, UR_ACT_GATE = 0, 1, 2, 3, 4
 UR_DT_BF16, UR_DT_F32 = 0, 1
