@@ -37,6 +37,7 @@ class ControlledUNet(UrModule):
         else:
             raise ValueError(f"control_type '{control_type}' not supported")
         self._ctx = None
+        self._cross = None
         self._sc_streams = {}
         self.overlap_sc_tuner = os.environ.get("UNIRESTORE_OVERLAP_SCTUNER", "1") == "1"
 
@@ -49,6 +50,15 @@ class ControlledUNet(UrModule):
         if self._ctx is None or self._ctx.device != self.null_embeds.device:
             self._ctx = self.null_embeds.detach().to(torch.bfloat16).contiguous()
         return self._ctx
+
+    def begin_forward(self):
+        """Drop the cross-attention K/V of the null prompt: they are recomputed (32 small GEMMs) at first use in every
+        forward, so a timed forward carries no precomputed activations."""
+        if self._cross is None:
+            from .sd_blocks import Attention
+            self._cross = [m for m in self.unet.modules() if isinstance(m, Attention) and m.is_cross]
+        for m in self._cross:
+            m._ctx_ref, m._ctx_kv = None, None
 
     def time_embed(self, timesteps):
         u = self.unet

@@ -108,6 +108,19 @@ class TimestepEmbedding(UrModule):
         return ops.small_linear(h, p["w2"], p["b2"])
 
 
+class TimeCtx:
+    """Time embeddings of ONE forward: ``emb`` fp32 [T, D] for the T scheduler timesteps (computed at the start of every
+    forward, inside the timed region -- nothing input-independent is carried over between forwards except packed
+    weights), ``index`` = current DDIM step.  ``proj`` holds each ResnetBlock's ``time_emb_proj(silu(emb))`` [T, C],
+    filled by one launch per block at first use; ``at(i)`` shares both with a different step index."""
+
+    def __init__(self, emb, index=0, proj=None):
+        self.emb, self.index, self.proj = emb, index, ({} if proj is None else proj)
+
+    def at(self, index):
+        return TimeCtx(self.emb, index, self.proj)
+
+
 # ------------------------------------------------------------------------------------------------- resnet
 class ResnetBlock2D(UrModule):
     """GN -> SiLU -> conv3x3 (+time_emb_proj(silu(temb))) -> GN -> SiLU -> conv3x3 (+1x1 shortcut) + input.
@@ -137,20 +150,20 @@ class ResnetBlock2D(UrModule):
         return p
 
     def run(self, x, temb=None, x2=None):
-        """x (and optional channel-concatenated x2) bf16 NHWC; temb fp32 [1 or B, temb_channels]."""
+        """x (and optional channel-concatenated x2) bf16 NHWC; temb fp32 [1 or B, temb_channels] or a ``TimeCtx``."""
         p = self.pk
         co = self.out_channels
         h = ops.group_norm(x, self.groups, p["g1"], p["b1"], self.eps, silu=True, x2=x2)
         tvec = None
         if temb is not None and self.time_emb_proj is not None:
-            # time_emb_proj(silu(temb)) only depends on the (cached, per-timestep) embedding tensor: computed once
-            cache = p.setdefault("tvec", {})
-            hit = cache.get(id(temb))
-            if hit is None or hit[0] is not temb:
-                if len(cache) > 64:
-                    cache.clear()
-                hit = cache[id(temb)] = (temb, ops.small_linear(temb, p["wt"], p["tb"], act_in="silu"))
-            tvec = hit[1]
+            if isinstance(temb, TimeCtx):
+                # all T scheduler timesteps are projected in ONE launch at first use in this forward, then sliced
+                pr = temb.proj.get(id(self))
+                if pr is None:
+                    pr = temb.proj[id(self)] = ops.small_linear(temb.emb, p["wt"], p["tb"], act_in="silu")
+                tvec = pr[temb.index:temb.index + 1]
+            else:
+                tvec = ops.small_linear(temb, p["wt"], p["tb"], act_in="silu")
         # want_stats: the GEMM epilogue accumulates the statistics of the GroupNorm that consumes its output
         h = ops.conv_gemm(h, p["w1"], co, taps=TAPS_3x3, bias=p["c1b"], rowvec=tvec, want_stats=True)
         h = ops.group_norm(h, self.groups, p["g2"], p["b2"], self.eps, silu=True)

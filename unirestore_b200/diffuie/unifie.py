@@ -18,7 +18,7 @@ from .autoencoder import SkipConnectedAutoEncoder
 from .base_model import ControlledUNet
 from .controller import Controller, stablesr_config
 from .schedulers import DDIMScheduler, DDPMScheduler
-from .sd_blocks import AutoencoderKL, UNet2DConditionModel
+from .sd_blocks import AutoencoderKL, TimeCtx, UNet2DConditionModel
 
 
 class DiffUIE(nn.Module):
@@ -38,7 +38,7 @@ class DiffUIE(nn.Module):
             self.ddpm = DDPMScheduler.from_pretrained("stabilityai/sd-turbo", subfolder="scheduler")
             self.scheduler = DDIMScheduler.from_pretrained("stabilityai/sd-turbo", subfolder="scheduler")
             self.scheduler.set_timesteps(cnet["num_inference_steps"], device=self.train_timesteps.device)
-        self._temb_cache = {}
+        self._ts_dev = {}
         self._side_streams = {}
         self.overlap_controller = os.environ.get("UNIRESTORE_OVERLAP_CONTROLLER", "1") == "1"
         self.split_unet = os.environ.get("UNIRESTORE_SPLIT_UNET", "0") == "1"
@@ -67,16 +67,17 @@ class DiffUIE(nn.Module):
                                                    noise[i:i + 1].float().contiguous(), sb)
         return out, noise, timesteps
 
-    def _embeddings(self, t: int, device):
-        """Controller / UNet timestep embeddings of integer timestep t (cached: they only depend on weights)."""
-        key = (int(t), str(device))
-        if key not in self._temb_cache:
-            ts = torch.tensor([int(t)], dtype=torch.int64, device=device)
-            self._temb_cache[key] = (self.controller.time_embed(ts), self.base_model.time_embed(ts))
-        return self._temb_cache[key]
+    def _time_contexts(self, ts, device):
+        """(Controller, UNet) ``TimeCtx`` for the integer timesteps ``ts`` of this forward: one sinusoid + MLP launch
+        set per network over all T timesteps (base_model.py:104-106, controller.py:196-197)."""
+        key = (tuple(ts), str(device))
+        t_dev = self._ts_dev.get(key)
+        if t_dev is None:               # host -> device copy of the timestep list: once per (schedule, device)
+            t_dev = self._ts_dev[key] = torch.tensor(list(ts), dtype=torch.int64, device=device)
+        return TimeCtx(self.controller.time_embed(t_dev)), TimeCtx(self.base_model.time_embed(t_dev))
 
     def clear_caches(self):
-        self._temb_cache = {}
+        self._ts_dev = {}
         self._graphs = {}
         for m in self.modules():
             if hasattr(m, "invalidate"):
@@ -89,23 +90,26 @@ class DiffUIE(nn.Module):
             st = self._side_streams[key] = torch.cuda.Stream(device=device)
         return st
 
-    def _run_controller(self, z0_8, t: int):
-        emb_c, _ = self._embeddings(t, z0_8.device)
+    def _run_controller(self, z0_8, tctx):
         ops.stats_arena_begin(z0_8.device, "ctl")    # one fill instead of a memset node per GroupNorm
         try:
-            return self.controller.run(z0_8, emb_c)                              # unifie.py:148
+            return self.controller.run(z0_8, tctx)                               # unifie.py:148
         finally:
             ops.stats_arena_end(z0_8.device)
 
-    def _run_unet(self, zt8, control, t: int, role="main"):
-        _, emb_u = self._embeddings(t, zt8.device)
+    def _run_unet(self, zt8, control, tctx, role="main"):
         ops.stats_arena_begin(zt8.device, role)
         try:
-            return self.base_model.run(zt8, control, emb_u)                      # unifie.py:149
+            return self.base_model.run(zt8, control, tctx)                       # unifie.py:149
         finally:
             ops.stats_arena_end(zt8.device)
 
-    def _run_unet_split(self, zt8, control, t: int, main):
+    def predict_eps(self, zt8, z0_8, t: int):
+        ctx_c, ctx_u = self._time_contexts([int(t)], zt8.device)
+        self.base_model.begin_forward()
+        return self._run_unet(zt8, self._run_controller(z0_8, ctx_c), ctx_u)
+
+    def _run_unet_split(self, zt8, control, tctx, main):
         """The UNet on two half batches, the second on its own stream: images are independent, and two chains of
         small dependent kernels fill each other's idle SM time (tails, prologues, underfilled grids)."""
         B = zt8.shape[0]
@@ -113,17 +117,14 @@ class DiffUIE(nn.Module):
         s2 = self._stream("unet2", zt8.device)
         s2.wait_stream(main)
         with torch.cuda.stream(s2):
-            e2 = self._run_unet(zt8[h:], {k: v[h:] for k, v in control.items()}, t, role="unet2")
-        e1 = self._run_unet(zt8[:h], {k: v[:h] for k, v in control.items()}, t)
+            e2 = self._run_unet(zt8[h:], {k: v[h:] for k, v in control.items()}, tctx, role="unet2")
+        e1 = self._run_unet(zt8[:h], {k: v[:h] for k, v in control.items()}, tctx)
         main.wait_stream(s2)
         self._keep.append(e2)                      # produced on s2, consumed on main: kept alive until the loop ends
         eps = torch.empty((B,) + tuple(e1.shape[1:]), device=e1.device, dtype=e1.dtype)
         eps[:h].copy_(e1)
         eps[h:].copy_(e2)
         return eps
-
-    def predict_eps(self, zt8, z0_8, t: int):
-        return self._run_unet(zt8, self._run_controller(z0_8, t), t)
 
     def predict_z0(self, latents, conditions, timesteps):                        # unifie.py:91-105
         """One-step estimate of z0 from noisy latents; ``timesteps`` int64 [1] or [B] (per-sample, as drawn by
@@ -161,6 +162,8 @@ class DiffUIE(nn.Module):
         # of step i and fills the SMs its many small, dependent kernels leave idle (tails / prologues / underfilled
         # grids).  Its outputs are kept alive until the loop ends, so no buffer crosses streams while being recycled.
         ts = [int(t) for t in self.scheduler.timesteps_host]
+        ctx_c, ctx_u = self._time_contexts(ts, z0.device)      # all T time embeddings of this forward, two launch sets
+        self.base_model.begin_forward()                        # null-prompt K/V are recomputed in this forward
         main = torch.cuda.current_stream(z0.device)
         side = self._stream("ctl", z0.device)
         overlap = self.overlap_controller and len(ts) > 1
@@ -169,11 +172,11 @@ class DiffUIE(nn.Module):
 
         def launch_controller(i):
             if not overlap:
-                return self._run_controller(z0_8, ts[i]), None
+                return self._run_controller(z0_8, ctx_c.at(i)), None
             if i == 0:
                 side.wait_stream(main)                                            # z0_8 is produced on the main stream
             with torch.cuda.stream(side):
-                ctl = self._run_controller(z0_8, ts[i])
+                ctl = self._run_controller(z0_8, ctx_c.at(i))
                 ev = torch.cuda.Event()
                 ev.record(side)
             keep.append(ctl)
@@ -186,7 +189,8 @@ class DiffUIE(nn.Module):
                 nxt = launch_controller(i + 1)
             if ev is not None:
                 main.wait_event(ev)
-            eps8 = self._run_unet_split(zt8, control, t, main) if split else self._run_unet(zt8, control, t)
+            eps8 = (self._run_unet_split(zt8, control, ctx_u.at(i), main) if split
+                    else self._run_unet(zt8, control, ctx_u.at(i)))
             zt8 = ops.ddim_step_(zt, eps8, self.scheduler.step_coefficients(t), bool(self.scheduler.config.clip_sample))
         if overlap:
             main.wait_stream(side)
