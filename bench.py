@@ -213,6 +213,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = (CFG[0], dict(CFG[1], num_inference_steps=a.ddim_steps), CFG[2])
     model = cheap_init_(DiffUIE(*cfg)).eval().requires_grad_(False).to(dev)
