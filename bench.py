@@ -162,6 +162,19 @@ def run_reference(a):
     }))
 
 
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries write to file descriptor 1 behind Python's back (NCCL
+    prints "NCCL version ..." there when the first communicator is created).  Point fd 1 at stderr for the rest of the
+    process and return a writer for the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text):
+        os.write(real, (text.rstrip("\n") + "\n").encode())
+    return emit
+
+
 # ------------------------------------------------------------------------------------------------ ours
 def kernel_roofline(dev):
     """The dominant kernel (tcgen05 implicit-GEMM conv, UNet 320->320 3x3 @64x64, B=8: 60.4 GFLOP per launch)
@@ -202,6 +215,7 @@ def kernel_roofline(dev):
 
 
 def run_ours(a):
+    emit = claim_stdout()
     import torch.distributed as dist
     from unirestore_b200 import _cabi
     from unirestore_b200.diffuie import DiffUIE
@@ -213,8 +227,6 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output ("NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = (CFG[0], dict(CFG[1], num_inference_steps=a.ddim_steps), CFG[2])
     model = cheap_init_(DiffUIE(*cfg)).eval().requires_grad_(False).to(dev)
@@ -306,7 +318,7 @@ def run_ours(a):
             except Exception as ex:   # the oracle is test infrastructure; never let it break the GPU numbers
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: %r" % (ex,)}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

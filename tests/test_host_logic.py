@@ -1,5 +1,7 @@
 """Host-side logic of the product path that needs no GPU: state_dict contract against the oracle / reference keys,
 weight packing (gated interleave, sub-pixel upsample weights, block-diagonal grouped conv), config validation."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -145,3 +147,16 @@ def test_reference_checkpoint_surgery(model):
     assert float(model.ae.vae.encoder.fr_blocks[0][0].conv1.weight.mean()) == 0.5   # CFRM kept
     with pytest.raises(RuntimeError):
         load_sd_turbo(model, None, {k: v for k, v in vae_sd.items() if k != "quant_conv.weight"})
+
+
+def test_bench_stdout_carries_only_the_json_line(tmp_path):
+    """bench.claim_stdout(): library writes to fd 1 (NCCL's version banner) end up on stderr, the JSON line on stdout."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys, json; sys.path.insert(0, %r); import bench; emit = bench.claim_stdout(); "
+            "os.write(1, b'NCCL version 2.28.9\\n'); print('stray print'); emit(json.dumps({'ok': 1}))" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"ok": 1}\n'
+    assert "NCCL version" in r.stderr and "stray print" in r.stderr
