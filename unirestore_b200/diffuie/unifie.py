@@ -11,7 +11,6 @@ import os
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from .. import ops
 from .autoencoder import SkipConnectedAutoEncoder
@@ -222,13 +221,9 @@ class DiffUIE(nn.Module):
             h, w = round(h * s), round(w * s)
         pad_r, pad_b = (64 - w % 64) % 64, (64 - h % 64) % 64                     # unifie.py:130-134
         if resize or pad_r or pad_b:
-            if images.is_cuda:      # bicubic resize + reflect pad in one kernel
-                images = ops.resize_pad(images, (h, w) if resize else None, pad_b, pad_r)
-            else:                   # (CPU tensors only reach the error paths of the ops below)
-                if resize:
-                    images = F.interpolate(images, (h, w), mode="bicubic", align_corners=False, antialias=False)
-                if pad_r or pad_b:
-                    images = F.pad(images, (0, pad_r, 0, pad_b), mode="reflect")
+            if not images.is_cuda:
+                raise ValueError("DiffUIE.forward needs CUDA tensors (the product path has no CPU fallback)")
+            images = ops.resize_pad(images, (h, w) if resize else None, pad_b, pad_r)   # one gather kernel
         n_post, n_diff = noise if noise is not None else (None, None)
         z0, z0_8, mids = self.ae.run_encode(images, enable_fr=self.fr_type is not None, noise=n_post)
         zt = self.restore_latents(z0, z0_8, n_diff) if self.control_type else z0
