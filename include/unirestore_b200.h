@@ -199,16 +199,24 @@ int ur_ddim_step(float* x, const float* eps, int ld_eps, float sqrt_alpha_t, flo
 /* out bf16 [B,H,W,8] = a*img + b for the first `channels`, zeros after (autoencoder.py:151 `x*2-1`). */
 int ur_image_to_nhwc8(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels, int h,
                       int w, float a, float b, void* out, void* stream);
-/* out fp32 [B,C,h,w] = a*src[:, :h, :w, :C] + b (autoencoder.py:175 `(x+1)/2`, crop of unifie.py:164). */
-int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w, float a, float b,
-                     float* out, void* stream);
+/* out fp32 [B,C,h,w] = q(a*src[:, y0:y0+h, x0:x0+w, :C] + b) (autoencoder.py:175 `(x+1)/2`, crop of unifie.py:164);
+ * quantize != 0: q(v) = clamp(round(255 v), 0, 255) / 255, the 8-bit quantisation the validate loop applies to every
+ * prediction (eval_image_restoration.py:71), fused into the image write-out. */
+int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w, int y0, int x0,
+                     float a, float b, int quantize, float* out, void* stream);
+
+/* out[r, :] = cat(x1[r, :c1], x2[r, :c2]) on bf16 rows -- torch.cat(dim=1) of base_model.py:189,197 materialised; only
+ * used when source 1 of a two-source convolution is not 64-channel aligned (never on the sd-turbo shapes). */
+int ur_concat_channels(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int64_t rows, void* out,
+                       void* stream);
 
 /* Image pre / post around the path (unifie.py:124-134,165-168): out = reflect_pad_{bottom,right}(bicubic_resize(img,
  * (hr, wr))) on fp32 NCHW (arbitrary input strides in elements), F.interpolate(mode="bicubic", align_corners=False,
  * antialias=False) + F.pad(mode="reflect") semantics; hr == hin && wr == win skips the resize.
- * out: dense fp32 [batch, channels, hr + pad_b, wr + pad_r]. */
+ * out: dense fp32 [batch, channels, hr + pad_b, wr + pad_r]; quantize != 0 applies the 8-bit quantisation of
+ * eval_image_restoration.py:71 to the result (the resize back to the input resolution is the last op of the path). */
 int ur_resize_pad(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels, int hin,
-                  int win, int hr, int wr, int pad_b, int pad_r, float* out, void* stream);
+                  int win, int hr, int wr, int pad_b, int pad_r, int quantize, float* out, void* stream);
 
 /* Metrics step right after the path (eval_image_restoration.py:71,255-313: 8-bit quantisation of the prediction,
  * skimage peak_signal_noise_ratio / structural_similarity(win 7, uniform, sample covariance, channel_axis 0)):

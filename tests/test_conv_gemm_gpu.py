@@ -219,8 +219,9 @@ def test_gated_and_linear_pair_modes(pair_mode, mode):
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 8, 8, 1280, 1280), (8, 8, 8, 2560, 1280), (3, 8, 8, 512, 512),
                                             (1, 16, 16, 1280, 320)])
 def test_conv3x3_split_k(B, H, W, Cin, Cout):
-    """Few output tiles + long K: the K range is split over CTAs (fp32 red.global.add into the caller's workspace +
-    finishing kernel with bias / temb row vector / residual); compared with torch and with the unsplit kernel."""
+    """Few output tiles + long K: the K range is split over CTAs (one fp32 slab per K slice in the caller's workspace,
+    plain stores; the finishing kernel adds the slabs in a fixed order with bias / temb row vector / residual);
+    compared with torch and with the unsplit kernel, and run twice: bit-identical (no atomics on the data path)."""
     from unirestore_b200 import _cabi, ops
     x = _rand(B, Cin, H, W, seed=100)
     w = _rand(Cout, Cin, 3, 3, seed=101, scale=(9 * Cin) ** -0.5)
@@ -238,14 +239,19 @@ def test_conv3x3_split_k(B, H, W, Cin, Cout):
     finally:
         _cabi.lib().ur_debug_set_gemm_splitk(old)
     assert_close(y, y0, 2e-3, "split-K vs unsplit")
+    y2 = ops.conv_gemm(xb, wp, Cout, taps=ops.TAPS_3x3, bias=b, rowvec=tv, residual=r)
+    assert torch.equal(y, y2), "split-K is not bit-reproducible"
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(2, 16, 16, 64, 320, 9), (1, 24, 40, 128, 320, 9), (3, 8, 8, 320, 640, 9),
                                                  (8, 8, 8, 1280, 1280, 9), (2, 64, 64, 320, 320, 1),
-                                                 (5, 4, 4, 256, 200, 9), (1, 20, 136, 64, 128, 9)])
+                                                 (5, 4, 4, 256, 200, 9), (1, 20, 136, 64, 128, 9),
+                                                 (8, 8, 8, 1280, 1280, 1), (7, 8, 8, 640, 320, 1), (6, 4, 8, 128, 256, 1),
+                                                 (3, 8, 4, 192, 320, 9)])
 def test_epilogue_group_norm_statistics(B, H, W, Cin, Cout, taps):
-    """want_stats: the (sum, sumsq) per (image, channel) accumulated by the GEMM epilogue (or its fall-backs for tiles
-    spanning images / split-K) equal a ur_chan_stats pass over the finished output."""
+    """want_stats: the (sum, sumsq) per (image, channel) accumulated by the GEMM epilogue (tiles holding 1, 2 or 4
+    whole images, odd batch counts), by the split-K finishing kernel, or by the fall-back pass (more than 4 images per
+    tile) equal a ur_chan_stats pass over the finished output."""
     from unirestore_b200 import ops
     x = _rand(B, Cin, H, W, seed=110)
     k = 3 if taps == 9 else 1

@@ -79,8 +79,9 @@ SIGNATURES = {
     "ur_ddim_step": (C.c_int, [_P, _P, _I, _F, _F, _F, _F, _I, _I, _I, _P, _P]),
     "ur_image_to_nhwc8": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I, _I, _I, _I, _F, _F, _P, _P]),
     "ur_image_metrics": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
-    "ur_resize_pad": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "ur_nhwc_to_image": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "ur_resize_pad": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "ur_nhwc_to_image": (C.c_int, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _I, _P, _P]),
+    "ur_concat_channels": (C.c_int, [_P, _I64, _I, _P, _I64, _I, _I64, _P, _P]),
 }
 
 _lib = None
@@ -101,11 +102,13 @@ def lib():
 
 
 launch_count = 0          # C-ABI compute calls issued (each is >= 1 kernel launch); read by bench.py
+launch_counts = {}        # the same, per entry point (launches-per-DDIM-step reports)
 
 
 def check(rc: int, what: str = ""):
     global launch_count
     launch_count += 1
+    launch_counts[what] = launch_counts.get(what, 0) + 1
     if rc != 0:
         raise UrError("%s failed (%d): %s" % (what or "unirestore_b200 call", rc,
                                               lib().ur_last_error().decode(errors="replace")))

@@ -405,7 +405,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   const bool split_ok = g_split_mode != 0 && d->workspace && !(reinterpret_cast<uintptr_t>(d->workspace) & 15) && !gated &&
                         d->act == UR_ACT_NONE && d->alpha == 1.0f && !d->chscale && !d->w_batched && !d->group_kc &&
                         d->out_dtype == UR_DT_BF16 && d->n % 8 == 0 && !d->bn && best_cost <= 8 && nkb_total >= 64 &&
-                        4LL * m_rows * d->n <= d->workspace_bytes;
+                        2 * 4LL * m_rows * d->n <= d->workspace_bytes;
   int bn = 0;
   bool pair = false;
   pick_tile_config(d->n, best_cost, d->ntaps * (((d->group_kc ? d->group_kc : ctot) + 63) / 64), d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : 0),
@@ -535,7 +535,8 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     }
     // GroupNorm statistics of the output: fused into the epilogue when an M tile never spans two images and K is not
     // split; otherwise a ur_chan_stats pass over the finished output (dense pixel pitch required) does the same
-    const bool stats_fused = d->stats && Bt == 1 && !split_ok;
+    // (an M tile may hold Bt = 1, 2 or 4 whole images: every 32-row quarter of the tile then lies inside one image)
+    const bool stats_fused = d->stats && Bt <= 4;
     if (stats_fused) {
       p.stats = d->stats + 2LL * d->stats_off;
       p.stats_ld = d->stats_ld;
@@ -554,17 +555,22 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
       int s = static_cast<int>(num_sms() / (ctas > 0 ? ctas : 1));
       if (s > nkb_total / 16) s = nkb_total / 16;
       if (s > 8) s = 8;
-      if (s >= 2) {
+      while (s >= 2 && 4LL * s * m_rows * d->n > d->workspace_bytes) --s;      // one fp32 slab per K slice
+      const bool finish_stats_ok = !d->stats || 2ULL * d->n * ((d->n >> 3) >= 256 ? 1 : 256 / (d->n >> 3)) * 4 <= 48 * 1024;
+      if (s >= 2 && finish_stats_ok) {
         p.ksplit = s;
         p.fd_ksplit = make_fastdiv(static_cast<uint32_t>(s));
         p.ws = static_cast<float*>(d->workspace);
-        cudaError_t e = cudaMemsetAsync(d->workspace, 0, 4ULL * m_rows * d->n, stream);
-        if (e != cudaSuccess) return set_cuda_error(e, "ur_conv_gemm split-K memset");
-        int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total * s), n_tiles, stream);
+        p.ws_slab = m_rows * d->n;
+        GemmParams pm = p;
+        pm.stats = nullptr;                       // the main kernel only writes partial tiles
+        int rc = launch_conv_gemm_persistent(pm, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total * s), n_tiles, stream);
         if (rc) return rc;
-        rc = launch_splitk_finish(p, stream);
-        if (rc || !d->stats) return rc;
-        return stats_fallback(d, n_out, stream);
+        if (d->stats) {                           // statistics of the finished bf16 output, fused into the finish pass
+          p.stats = d->stats + 2LL * d->stats_off;
+          p.stats_ld = d->stats_ld;
+        }
+        return launch_splitk_finish(p, stream);
       }
     }
     int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total), n_tiles, stream);

@@ -59,7 +59,8 @@ struct GemmParams {
   int stats_ld;       //   statistics fused into the epilogue); channel n of image b at stats[(b * stats_ld + n) * 2]
   int tma_store;      // persistent kernel: 1 = epilogue sub-blocks leave through TMA stores (mapOut), 0 = coalesced st.global
   int ksplit;         // split-K factor (1 = off); work unit u -> (tile u / ksplit, K slice u % ksplit)
-  float* ws;          // split-K: dense fp32 [B*Ho*Wo, N] partial sums (red.global.add), epilogue deferred to splitk_finish
+  float* ws;          // split-K: fp32 [ksplit][B*Ho*Wo, N] partial-sum slabs (plain stores), epilogue deferred to splitk_finish
+  long long ws_slab;  // elements per slab = B*Ho*Wo*N
   long long* trace;   // development: per-role clock64 timestamps of CTA 0 (nullptr = off)
 };
 

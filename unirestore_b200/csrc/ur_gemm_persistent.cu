@@ -333,15 +333,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       const int nout0 = gated ? (tc.n0 >> 1) : tc.n0;
       const int as = it & 1;
       if (p.ws) {
-        // ---- split-K: add this unit's fp32 partial tile into the workspace (vector reductions, 16 B each); bias /
-        //      residual / bf16 conversion happen once in splitk_finish_kernel
+        // ---- split-K: this unit's fp32 partial tile goes to slab `ks` of the workspace with plain 16-byte stores
+        //      (every element of every slab is written exactly once: no zero fill, no atomics, and the sum order in
+        //      splitk_finish_kernel is fixed -> bit-reproducible); bias / residual / bf16 conversion / GroupNorm
+        //      statistics happen once in splitk_finish_kernel
         mbar_wait(&tfull_bar[as], (it >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
         const int x = tc.x0 + (r & (Wt - 1)), y = tc.y0 + ((r >> p.wt_log2) & (Ht - 1));
         const int b = tc.b0 + (r >> (p.wt_log2 + p.ht_log2));
         const bool ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
-        float* wrow = p.ws + (static_cast<long long>(b * p.Ho + y) * p.Wo + x) * p.N + tc.n0;
+        const int ksl = t - fast_div(t, p.fd_ksplit) * ksplit;
+        float* wrow = p.ws + ksl * p.ws_slab + (static_cast<long long>(b * p.Ho + y) * p.Wo + x) * p.N + tc.n0;
         for (int c = grp * 32; c < BN; c += 64) {
           uint32_t va[32];
           tmem_ld32(trow + c, va);
@@ -350,8 +353,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (tc.n0 + c + 4 * j + 4 <= p.N)
-                red_add_v4_f32(wrow + c + 4 * j, __uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
-                               __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
+                *reinterpret_cast<float4*>(wrow + c + 4 * j) =
+                    make_float4(__uint_as_float(va[4 * j]), __uint_as_float(va[4 * j + 1]),
+                                __uint_as_float(va[4 * j + 2]), __uint_as_float(va[4 * j + 3]));
             }
           }
         }
@@ -515,8 +519,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           // ---- fused GroupNorm statistics: column sums / sums of squares of the bf16 tile just staged.  Thread gt
           //      takes column (gt & 31) over rows 32 * (gt >> 5) .. + 31 (one conflict-free 2-byte LDS per row; the
           //      swizzle only depends on (row >> 1) & 3, so four base pointers cover all rows); the four row quarters
-          //      meet in shared memory and one warp adds them to the fp64 statistics of image tc.b0 (M tiles never
-          //      span images here: Bt == 1)
+          //      meet in shared memory and one warp adds them to the fp64 statistics of the image(s) of the tile
           const int scol = gt & 31, sq4 = gt >> 5;
           const uint8_t* sb0 = stg + sq4 * 32 * 64 + (scol & 7) * 2;
           const int ch = scol >> 3;
@@ -546,12 +549,24 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           sred[gt] = make_float2(s1, s2);
           group_barrier(8 + grp);
           if (gt < 32) {
-            const float2 a0 = sred[gt], a1 = sred[gt + 32], a2 = sred[gt + 64], a3 = sred[gt + 96];
+            // the four 32-row quarters belong to Bt = 1, 2 or 4 consecutive images (a quarter never spans two: the
+            // host only fuses the statistics when an image contributes >= 32 rows to the tile)
             const int ncol = nout0 + c + gt;
-            if (ncol < n_out && tc.b0 < p.B) {
-              double* sp = p.stats + (static_cast<long long>(tc.b0) * p.stats_ld + ncol) * 2;
-              atomicAdd(sp, static_cast<double>((a0.x + a1.x) + (a2.x + a3.x)));
-              atomicAdd(sp + 1, static_cast<double>((a0.y + a1.y) + (a2.y + a3.y)));
+            const int qpi = 4 / Bt;                 // quarters per image
+            if (ncol < n_out) {
+              for (int bi = 0; bi < Bt; ++bi) {
+                float t1 = 0.f, t2 = 0.f;
+                for (int qq = bi * qpi; qq < (bi + 1) * qpi; ++qq) {
+                  const float2 a = sred[gt + 32 * qq];
+                  t1 += a.x;
+                  t2 += a.y;
+                }
+                if (tc.b0 + bi < p.B) {
+                  double* sp = p.stats + (static_cast<long long>(tc.b0 + bi) * p.stats_ld + ncol) * 2;
+                  atomicAdd(sp, static_cast<double>(t1));
+                  atomicAdd(sp + 1, static_cast<double>(t2));
+                }
+              }
             }
           }
         }
@@ -573,29 +588,41 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   }
 }
 
-// out[b, y, x, n] = bf16(ws[m, n] + bias[n] + rowvec[b, n] + residual[b, y, x, n]); 8 channels per thread
-__global__ void splitk_finish_kernel(const GemmParams p) {
+// out[b, y, x, n] = bf16(sum_ks ws[ks][m, n] + bias[n] + rowvec[b, n] + residual[b, y, x, n]), slabs added in ks order.
+// grid (chunks, B), block CV * PL threads: thread (cv, pl) owns 8 channels and pixels p0+pl, p0+pl+PL, ... of image b;
+// with p.stats the per-(image, channel) sum / sum of squares of the bf16 output (GroupNorm statistics of the consumer)
+// are reduced like ur_chan_stats (per-lane partial rows in shared memory, fixed order) and added in fp64.
+__global__ void splitk_finish_kernel(const GemmParams p, int CV, int PL, int chunk) {
   pdl_launch_dependents();
   pdl_wait();
-  const int nv = p.N >> 3;
-  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * nv;
+  extern __shared__ __align__(16) float sh[];   // [PL][2][N] (statistics only)
+  const int b = blockIdx.y;
+  const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  const int P = p.Ho * p.Wo;
+  const int p0 = blockIdx.x * chunk, p1 = min(P, p0 + chunk);
   bf16* outp = reinterpret_cast<bf16*>(p.out);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % nv);
-    const long long m = i / nv;
-    const int x = static_cast<int>(m % p.Wo);
-    const int y = static_cast<int>((m / p.Wo) % p.Ho);
-    const int b = static_cast<int>(m / (static_cast<long long>(p.Wo) * p.Ho));
-    const float4 a0 = *reinterpret_cast<const float4*>(p.ws + m * p.N + cv * 8);
-    const float4 a1 = *reinterpret_cast<const float4*>(p.ws + m * p.N + cv * 8 + 4);
-    float f[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  float add[8], s[8], q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = cv * 8 + j;
-      if (p.bias) f[j] += __ldg(p.bias + n);
-      if (p.rowvec) f[j] += __ldg(p.rowvec + b * p.rowvec_sb + n);
+  for (int j = 0; j < 8; ++j) {
+    const int n = cv * 8 + j;
+    add[j] = (p.bias ? __ldg(p.bias + n) : 0.f) + (p.rowvec ? __ldg(p.rowvec + b * p.rowvec_sb + n) : 0.f);
+    s[j] = q[j] = 0.f;
+  }
+  for (int pix = p0 + pl; pix < p1; pix += PL) {
+    const long long m = static_cast<long long>(b) * P + pix;
+    const int y = pix / p.Wo, x = pix - y * p.Wo;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    const float* wp = p.ws + m * p.N + cv * 8;
+    for (int ks = 0; ks < p.ksplit; ++ks, wp += p.ws_slab) {
+      const float4 a0 = *reinterpret_cast<const float4*>(wp);
+      const float4 a1 = *reinterpret_cast<const float4*>(wp + 4);
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+      f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += add[j];
     if (p.residual) {
       const uint4 rv = __ldg(reinterpret_cast<const uint4*>(p.residual + b * p.res_sb + y * p.res_sy + x * p.res_sx + cv * 8));
       const uint32_t u[4] = {rv.x, rv.y, rv.z, rv.w};
@@ -607,16 +634,49 @@ __global__ void splitk_finish_kernel(const GemmParams p) {
         f[2 * k + 1] += r1;
       }
     }
-    *reinterpret_cast<uint4*>(outp + b * p.out_sb + y * p.out_sy + x * p.out_sx + cv * 8) =
-        make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
+      float r0, r1;
+      unpack_bf16(o[k], r0, r1);                 // statistics of the ROUNDED output (what the consumer reads)
+      s[2 * k] += r0;
+      q[2 * k] = fmaf(r0, r0, q[2 * k]);
+      s[2 * k + 1] += r1;
+      q[2 * k + 1] = fmaf(r1, r1, q[2 * k + 1]);
+    }
+    *reinterpret_cast<uint4*>(outp + b * p.out_sb + y * p.out_sy + x * p.out_sx + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (p.stats) {
+    const int C = p.N;
+    float* row = sh + static_cast<size_t>(pl) * 2 * C + cv * 8;
+    *reinterpret_cast<float4*>(row) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(row + 4) = make_float4(s[4], s[5], s[6], s[7]);
+    *reinterpret_cast<float4*>(row + C) = make_float4(q[0], q[1], q[2], q[3]);
+    *reinterpret_cast<float4*>(row + C + 4) = make_float4(q[4], q[5], q[6], q[7]);
+    __syncthreads();
+    double* so = p.stats + static_cast<long long>(b) * p.stats_ld * 2;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      float t = 0.f;
+      for (int l = 0; l < PL; ++l) t += sh[static_cast<size_t>(l) * 2 * C + i];
+      const int c = i < C ? i : i - C;
+      atomicAdd(so + 2 * c + (i < C ? 0 : 1), static_cast<double>(t));
+    }
   }
 }
 
 int launch_splitk_finish(const GemmParams& p, cudaStream_t stream) {
-  const long long total = static_cast<long long>(p.B) * p.Ho * p.Wo * (p.N >> 3);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 4LL * num_sms()) blocks = 4LL * num_sms();
-  cudaError_t e = launch_kernel(splitk_finish_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, p);
+  const int CV = p.N >> 3;
+  if (CV > 1024) return set_error(UR_ERR_ARG, "splitk_finish: N too large");
+  const int PL = CV >= 256 ? 1 : 256 / CV;
+  const int P = p.Ho * p.Wo;
+  const int target = max(1, (2 * num_sms()) / (p.B > 0 ? p.B : 1));
+  int chunk = (P + target - 1) / target;
+  if (chunk < 2 * PL) chunk = 2 * PL;
+  const size_t smem = p.stats ? 2 * static_cast<size_t>(p.N) * PL * sizeof(float) : 0;
+  if (smem > 48 * 1024) return set_error(UR_ERR_ARG, "splitk_finish: statistics need too much shared memory");
+  cudaError_t e = launch_kernel(splitk_finish_kernel, dim3((P + chunk - 1) / chunk, p.B), dim3(CV * PL), smem, stream, p,
+                                CV, PL, chunk);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "splitk_finish launch");
 }
 

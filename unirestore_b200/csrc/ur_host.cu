@@ -83,10 +83,9 @@ int pdl_enabled() {
 using namespace ur;
 
 extern "C" int ur_init(int device) {
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) return set_cuda_error(e, "cudaSetDevice");
+  // no cudaSetDevice here: the caller (torch) owns the current device; callers make the tensor's device current
   cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, device);
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return set_cuda_error(e, "cudaGetDeviceProperties");
   if (prop.major != 10) return set_error(UR_ERR_CUDA, "unirestore_b200 requires an sm_100 GPU, found sm_%d%d", prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;

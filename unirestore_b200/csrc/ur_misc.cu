@@ -81,13 +81,12 @@ __global__ void dwconv3x3_gate_kernel(const bf16* __restrict__ x, int H, int W, 
                                       int CV, int PL, int chunk) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ __align__(16) float sh[];  // pooled[c] | weights transposed to [9][2c] (tap-major, 128-bit reads)
+  extern __shared__ __align__(16) float sh[];  // pooled[PL][c] | weights transposed to [9][2c] (tap-major, 128-bit reads)
   const int C2 = 2 * c;
   float* s_pool = sh;
-  float* s_w = sh + c;
+  float* s_w = sh + PL * c;
   const int b = blockIdx.y;
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < c; i += blockDim.x) s_pool[i] = 0.f;
   for (int i = threadIdx.x; i < 9 * C2; i += blockDim.x) s_w[(i % 9) * C2 + i / 9] = __ldg(wgt + i);
   __syncthreads();
   const int P = H * W;
@@ -151,11 +150,16 @@ __global__ void dwconv3x3_gate_kernel(const bf16* __restrict__ x, int H, int W, 
     }
     *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * P + p) * c + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
+  // per-pixel-lane partial rows summed in a fixed order (no shared-memory float atomics: their order, hence the
+  // fp32 rounding of the pooled vector, would change from run to run)
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&s_pool[cv * 8 + j], pool[j]);
+  for (int j = 0; j < 8; ++j) s_pool[pl * c + cv * 8 + j] = pool[j];
   __syncthreads();
-  for (int i = threadIdx.x; i < c; i += blockDim.x)
-    atomicAdd(stats + (static_cast<long long>(b) * c + i) * 2, static_cast<double>(s_pool[i]));
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float t = 0.f;
+    for (int l = 0; l < PL; ++l) t += s_pool[l * c + i];
+    atomicAdd(stats + (static_cast<long long>(b) * c + i) * 2, static_cast<double>(t));
+  }
 }
 
 // ------------------------------------------------------------------------------------ small_linear
@@ -411,9 +415,13 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
   w[2] = ((A + 2.0f) * u - (A + 3.0f)) * u * u + 1.0f;
   w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
 }
+// pred.mul(255).round_().clamp_(0, 255).div_(255) of the validate loop (eval_image_restoration.py:71); rintf rounds
+// half to even like torch.round
+__device__ __forceinline__ float quantize8(float v) { return fminf(fmaxf(rintf(v * 255.0f), 0.0f), 255.0f) / 255.0f; }
+
 __global__ void resize_pad_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy, long long sx,
                                   int C, int Hin, int Win, int Hr, int Wr, int Ho, int Wo, float scale_y, float scale_x,
-                                  long long total, float* __restrict__ out) {
+                                  int quantize, long long total, float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   const bool resize = Hr != Hin || Wr != Win;
@@ -449,14 +457,15 @@ __global__ void resize_pad_kernel(const float* __restrict__ img, long long sb, l
         v += wy[j] * row;
       }
     }
-    out[i] = v;
+    out[i] = quantize ? quantize8(v) : v;
   }
 }
 
 // fp32 channels-last [B,Hs,Ws,ld] -> fp32 NCHW [B,C,H,W] = a*x + b over the top-left HxW crop (autoencoder.py:175,
 // unifie.py:164)
-__global__ void nhwc_to_image_kernel(const float* __restrict__ src, int ld, int Hs, int Ws, int C, int H, int W,
-                                     float a, float bofs, long long total, float* __restrict__ out) {
+__global__ void nhwc_to_image_kernel(const float* __restrict__ src, int ld, int Hs, int Ws, int C, int H, int W, int y0,
+                                     int x0, float a, float bofs, int quantize, long long total,
+                                     float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -465,7 +474,26 @@ __global__ void nhwc_to_image_kernel(const float* __restrict__ src, int ld, int 
     const int yy = static_cast<int>((i / W) % H);
     const int c = static_cast<int>((i / (static_cast<long long>(W) * H)) % C);
     const long long b = i / (static_cast<long long>(W) * H * C);
-    out[i] = a * src[((b * Hs + yy) * Ws + xx) * ld + c] + bofs;
+    const float v = a * src[((b * Hs + yy + y0) * Ws + xx + x0) * ld + c] + bofs;
+    out[i] = quantize ? quantize8(v) : v;
+  }
+}
+
+// out[r, 0:c1] = x1[r, 0:c1], out[r, c1:c1+c2] = x2[r, 0:c2] on bf16 rows (16-byte vectors): the materialised channel
+// concat for two-source convolutions whose first source is not 64-channel aligned (reduced test topologies only;
+// the sd-turbo shapes read both sources through two TMA tensor maps and never come here)
+__global__ void concat_channels_kernel(const bf16* __restrict__ x1, long long ld1, int c1, const bf16* __restrict__ x2,
+                                       long long ld2, int c2, long long rows, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int nv = (c1 + c2) >> 3, nv1 = c1 >> 3;
+  const long long total = rows * nv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nv);
+    const long long r = i / nv;
+    const bf16* src = v < nv1 ? x1 + r * ld1 + v * 8 : x2 + r * ld2 + (v - nv1) * 8;
+    *reinterpret_cast<uint4*>(out + r * (c1 + c2) + v * 8) = __ldg(reinterpret_cast<const uint4*>(src));
   }
 }
 
@@ -509,7 +537,7 @@ extern "C" int ur_transpose_tokens(const void* x, int64_t ld, int64_t batch_stri
 extern "C" int ur_dwconv3x3_gate(const void* x, int batch, int h, int w, int c, const float* weight, const float* bias,
                                  void* y, double* stats, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!x || !weight || !bias || !y || !stats || c % 8 || 19 * static_cast<size_t>(c) * sizeof(float) > 48 * 1024)
+  if (!x || !weight || !bias || !y || !stats || c % 8 || (2048 + 18 * static_cast<size_t>(c)) * sizeof(float) > 48 * 1024)
     return set_error(UR_ERR_ARG, "ur_dwconv3x3_gate: bad arguments");
   cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * static_cast<size_t>(batch) * c, stream);
   if (e != cudaSuccess) return set_cuda_error(e, "ur_dwconv3x3_gate memset");
@@ -520,7 +548,7 @@ extern "C" int ur_dwconv3x3_gate(const void* x, int batch, int h, int w, int c, 
   int chunk = (P + target - 1) / target;
   if (chunk < PL * 2) chunk = PL * 2;
   dim3 grid((P + chunk - 1) / chunk, batch);
-  launch_kernel(dwconv3x3_gate_kernel, dim3(grid), dim3(CV * PL), (c + 18 * static_cast<size_t>(c)) * sizeof(float), stream, static_cast<const bf16*>(x), h, w, c, weight, bias,
+  launch_kernel(dwconv3x3_gate_kernel, dim3(grid), dim3(CV * PL), (static_cast<size_t>(PL) * c + 18 * static_cast<size_t>(c)) * sizeof(float), stream, static_cast<const bf16*>(x), h, w, c, weight, bias,
                                                                      static_cast<bf16*>(y), stats, CV, PL, chunk);
   UR_LAUNCH_CHECK("ur_dwconv3x3_gate");
 }
@@ -606,24 +634,37 @@ extern "C" int ur_image_to_nhwc8(const float* img, int64_t sb, int64_t sc, int64
   UR_LAUNCH_CHECK("ur_image_to_nhwc8");
 }
 
-extern "C" int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w,
-                                float a, float b, float* out, void* stream) {
-  if (!src || !out || h > hs || w > ws || channels > ld) return set_error(UR_ERR_ARG, "ur_nhwc_to_image: bad arguments");
+extern "C" int ur_nhwc_to_image(const float* src, int ld, int hs, int ws, int batch, int channels, int h, int w, int y0,
+                                int x0, float a, float b, int quantize, float* out, void* stream) {
+  if (!src || !out || y0 < 0 || x0 < 0 || y0 + h > hs || x0 + w > ws || channels > ld)
+    return set_error(UR_ERR_ARG, "ur_nhwc_to_image: bad arguments");
   const long long total = static_cast<long long>(batch) * channels * h * w;
-  launch_kernel(nhwc_to_image_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, ld, hs, ws, channels, h, w, a,
-                                                                                      b, total, out);
+  launch_kernel(nhwc_to_image_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, ld, hs,
+                ws, channels, h, w, y0, x0, a, b, quantize, total, out);
   UR_LAUNCH_CHECK("ur_nhwc_to_image");
 }
 
+extern "C" int ur_concat_channels(const void* x1, int64_t ld1, int c1, const void* x2, int64_t ld2, int c2, int64_t rows,
+                                  void* out, void* stream) {
+  if (!x1 || !x2 || !out || c1 <= 0 || c2 <= 0 || c1 % 8 || c2 % 8 || ld1 % 8 || ld2 % 8 || rows <= 0 ||
+      ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(out)) & 15))
+    return set_error(UR_ERR_ARG, "ur_concat_channels: channels / pitches must be multiples of 8, pointers 16-byte aligned");
+  launch_kernel(concat_channels_kernel, dim3(grid_for(rows * ((c1 + c2) >> 3))), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), static_cast<const bf16*>(x1), ld1, c1, static_cast<const bf16*>(x2), ld2,
+                c2, rows, static_cast<bf16*>(out));
+  UR_LAUNCH_CHECK("ur_concat_channels");
+}
+
 extern "C" int ur_resize_pad(const float* img, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int batch, int channels,
-                             int hin, int win, int hr, int wr, int pad_b, int pad_r, float* out, void* stream) {
+                             int hin, int win, int hr, int wr, int pad_b, int pad_r, int quantize, float* out,
+                             void* stream) {
   if (!img || !out || batch <= 0 || channels <= 0 || hin <= 0 || win <= 0 || hr <= 0 || wr <= 0 || pad_b < 0 || pad_r < 0 ||
       pad_b >= hr || pad_r >= wr)
     return set_error(UR_ERR_ARG, "ur_resize_pad: bad arguments (reflect padding must be smaller than the image)");
   const int ho = hr + pad_b, wo = wr + pad_r;
   const long long total = static_cast<long long>(batch) * channels * ho * wo;
   launch_kernel(resize_pad_kernel, dim3(grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), img, sb, sc, sy,
-                sx, channels, hin, win, hr, wr, ho, wo, static_cast<float>(hin) / hr, static_cast<float>(win) / wr, total,
-                out);
+                sx, channels, hin, win, hr, wr, ho, wo, static_cast<float>(hin) / hr, static_cast<float>(win) / wr, quantize,
+                total, out);
   UR_LAUNCH_CHECK("ur_resize_pad");
 }

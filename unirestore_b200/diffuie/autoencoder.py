@@ -82,8 +82,9 @@ class SkipConnectedAutoEncoder(nn.Module):
         z, z8 = ops.posterior_sample(moments, noise.float().contiguous(), float(self.vae.config["scaling_factor"]))
         return z, z8, skips
 
-    def run_decode(self, latents, skips, task, crop_hw=None):
-        """latents fp32 [B,4,h,w], skips bf16 NHWC, task key -> fp32 [B,3,H,W] = (decoder + 1) / 2."""
+    def run_decode(self, latents, skips, task, crop_hw=None, quantize=False):
+        """latents fp32 [B,4,h,w], skips bf16 NHWC, task key -> fp32 [B,3,H,W] = (decoder + 1) / 2.
+        ``quantize``: 8-bit quantisation of the prediction (eval_image_restoration.py:71) fused into the write-out."""
         dec, pk, vp = self.vae.decoder, self.vae.decoder.pk, self.vae.pk
         prompt = None
         if self.tedit_type:
@@ -105,7 +106,7 @@ class SkipConnectedAutoEncoder(nn.Module):
         x = ops.group_norm(x, dec.conv_norm_out.num_groups, pk["g"], pk["b"], dec.conv_norm_out.eps, silu=True)
         y = ops.conv_gemm(x, pk["w_out"], 8, taps=ops.TAPS_3x3, bias=pk["b_out"], out_dtype=torch.float32)
         h, w = crop_hw if crop_hw is not None else (y.shape[1], y.shape[2])
-        return ops.nhwc_to_image(y, dec.conv_out.out_channels, h, w, 0.5, 0.5)                # autoencoder.py:175
+        return ops.nhwc_to_image(y, dec.conv_out.out_channels, h, w, 0.5, 0.5, quantize=quantize)   # autoencoder.py:175
 
     # ---------------------------------------------------------------------------------- reference API
     def encode(self, images, enable_fr=False, noise=None):

@@ -82,7 +82,7 @@ class ControlledUNet(UrModule):
         # SC-Tuner (base_model.py:233-238) only touches the skips: the 12 adapters (36 small GEMMs) run on a side stream,
         # deepest skip first (the order the decoder consumes them), under the mid block's 8x8 kernels that leave most
         # SMs idle.  The decoder waits on one event per skip.
-        events = None
+        events, old_skips = None, None
         if self.overlap_sc_tuner and x.is_cuda:
             main = torch.cuda.current_stream(x.device)
             side = self._sc_streams.get(x.device)
@@ -90,7 +90,12 @@ class ControlledUNet(UrModule):
                 side = self._sc_streams[x.device] = torch.cuda.Stream(device=x.device)
             side.wait_stream(main)
             events = [None] * len(skips)
-            with torch.cuda.stream(side):
+            # The un-adapted skips (and ``x``, the deepest one) were allocated on the MAIN stream and are read by the
+            # adapters on the SIDE stream (GEMM operand and residual).  They must not return to the main-stream pool
+            # while the side stream may still read them: keep them referenced until the up blocks have waited on
+            # every event (function exit), when the main stream is ordered after all side-stream reads.
+            old_skips = list(skips)
+            with torch.cuda.stream(side), ops.workspace_role("sct"):      # own split-K workspace on this stream
                 for i in reversed(range(len(self.csc_editors))):
                     skips[i] = self.csc_editors[i].run(skips[i], control[skips[i].shape[2]])
                     events[i] = torch.cuda.Event()
@@ -110,7 +115,9 @@ class ControlledUNet(UrModule):
                     x = a.run(x, ctx)
             if blk.upsamplers is not None:
                 x = blk.upsamplers[0].run(x)
-        return u.run_head(x)                                               # base_model.py:206-208
+        eps = u.run_head(x)                                                # base_model.py:206-208
+        del old_skips               # (main has waited on every adapter event above: safe to recycle from here on)
+        return eps
 
     def forward(self, sample, control, timesteps):
         timesteps = torch.as_tensor(timesteps, device=sample.device).reshape(-1)

@@ -19,6 +19,15 @@ from ..ops import TAPS_3x3, TAPS_3x3_NOPAD, UR_ACT_GEGLU
 
 
 # ------------------------------------------------------------------------------------------------- base
+_WEIGHT_GEN = [0]
+
+
+def weight_generation() -> int:
+    """Bumped whenever any module drops its packed weights; CUDA graphs captured under an older generation replay
+    kernels that point at freed / stale weight buffers and must be re-captured (``DiffUIE._forward_graphed``)."""
+    return _WEIGHT_GEN[0]
+
+
 class UrModule(nn.Module):
     """nn.Module with a per-module cache of packed device weights (dropped on .to() / load_state_dict)."""
 
@@ -28,6 +37,7 @@ class UrModule(nn.Module):
         self.register_load_state_dict_post_hook(lambda m, _: m.invalidate())
 
     def invalidate(self):
+        _WEIGHT_GEN[0] += 1
         for m in self.modules():
             if isinstance(m, UrModule):
                 m._reset_cache()

@@ -40,12 +40,13 @@ class DiffUIE(nn.Module):
         self._ts_dev = {}
         self._side_streams = {}
         self.overlap_controller = os.environ.get("UNIRESTORE_OVERLAP_CONTROLLER", "1") == "1"
-        self.split_unet = os.environ.get("UNIRESTORE_SPLIT_UNET", "0") == "1"
         self._keep = []
         # CUDA-graph replay of the whole forward for static shapes (one capture per (shape, task, noise-mode));
         # every kernel behind the C-ABI is capture-safe (no allocation, no synchronisation).
         self.use_cuda_graph = os.environ.get("UNIRESTORE_CUDA_GRAPH", "0") == "1"
         self._graphs = {}
+        self._graph_gen = -1
+        self.latent_trace = None
 
     # ---------------------------------------------------------------------------------- training-time helpers
     def diffuse(self, latents, timesteps=None, noise=None):                      # unifie.py:77-89
@@ -96,8 +97,8 @@ class DiffUIE(nn.Module):
         finally:
             ops.stats_arena_end(z0_8.device)
 
-    def _run_unet(self, zt8, control, tctx, role="main"):
-        ops.stats_arena_begin(zt8.device, role)
+    def _run_unet(self, zt8, control, tctx):
+        ops.stats_arena_begin(zt8.device, "main")
         try:
             return self.base_model.run(zt8, control, tctx)                       # unifie.py:149
         finally:
@@ -107,23 +108,6 @@ class DiffUIE(nn.Module):
         ctx_c, ctx_u = self._time_contexts([int(t)], zt8.device)
         self.base_model.begin_forward()
         return self._run_unet(zt8, self._run_controller(z0_8, ctx_c), ctx_u)
-
-    def _run_unet_split(self, zt8, control, tctx, main):
-        """The UNet on two half batches, the second on its own stream: images are independent, and two chains of
-        small dependent kernels fill each other's idle SM time (tails, prologues, underfilled grids)."""
-        B = zt8.shape[0]
-        h = B // 2
-        s2 = self._stream("unet2", zt8.device)
-        s2.wait_stream(main)
-        with torch.cuda.stream(s2):
-            e2 = self._run_unet(zt8[h:], {k: v[h:] for k, v in control.items()}, tctx, role="unet2")
-        e1 = self._run_unet(zt8[:h], {k: v[:h] for k, v in control.items()}, tctx)
-        main.wait_stream(s2)
-        self._keep.append(e2)                      # produced on s2, consumed on main: kept alive until the loop ends
-        eps = torch.empty((B,) + tuple(e1.shape[1:]), device=e1.device, dtype=e1.dtype)
-        eps[:h].copy_(e1)
-        eps[h:].copy_(e2)
-        return eps
 
     def predict_z0(self, latents, conditions, timesteps):                        # unifie.py:91-105
         """One-step estimate of z0 from noisy latents; ``timesteps`` int64 [1] or [B] (per-sample, as drawn by
@@ -166,7 +150,6 @@ class DiffUIE(nn.Module):
         main = torch.cuda.current_stream(z0.device)
         side = self._stream("ctl", z0.device)
         overlap = self.overlap_controller and len(ts) > 1
-        split = self.split_unet and z0.shape[0] >= 2 and z0.shape[0] % 2 == 0
         keep = self._keep = []
 
         def launch_controller(i):
@@ -188,30 +171,40 @@ class DiffUIE(nn.Module):
                 nxt = launch_controller(i + 1)
             if ev is not None:
                 main.wait_event(ev)
-            eps8 = (self._run_unet_split(zt8, control, ctx_u.at(i), main) if split
-                    else self._run_unet(zt8, control, ctx_u.at(i)))
+            eps8 = self._run_unet(zt8, control, ctx_u.at(i))
             zt8 = ops.ddim_step_(zt, eps8, self.scheduler.step_coefficients(t), bool(self.scheduler.config.clip_sample))
+            if self.latent_trace is not None:              # parity runs: latents after every DDIM step (eager only)
+                self.latent_trace.append(zt.clone())
         if overlap:
             main.wait_stream(side)
         self._keep = []
         return zt
 
     @torch.no_grad()
-    def forward(self, images, task, noise=None):
+    def forward(self, images, task, noise=None, quantize=False):
         """images fp32 [B,3,H,W] in [0,1] -> restored fp32 [B,3,H,W].  ``noise=(posterior, diffuse)`` injects the two
-        RNG draws of the reference (autoencoder.py:152, unifie.py:87) for parity runs."""
+        RNG draws of the reference (autoencoder.py:152, unifie.py:87) for parity runs.  ``quantize=True`` fuses the
+        validate loop's ``pred.mul(255).round_().clamp_(0, 255).div_(255)`` (eval_image_restoration.py:71) into the
+        last kernel of the path.  ``images`` may be a strided view (e.g. the centre crop of
+        eval_image_restoration.py:113-134, ``center_crop`` below): the first kernel reads it in place."""
         if self.use_cuda_graph and images.is_cuda:
-            return self._forward_graphed(images, task, noise)
-        return self._forward_impl(images, task, noise)
+            return self._forward_graphed(images, task, noise, quantize)
+        return self._forward_impl(images, task, noise, quantize)
 
-    def _forward_graphed(self, images, task, noise):
-        key = (tuple(images.shape), task, noise is not None, str(images.device))
+    def _forward_graphed(self, images, task, noise, quantize=False):
+        # Captured graphs point at the packed bf16 weights: any UrModule.invalidate() (.to() / .half() / _apply /
+        # load_state_dict on this module OR any child, e.g. ``model.controller.load_state_dict`` as in
+        # engine_unifie.py:49-126) bumps the weight generation and the graphs recorded before it are dropped.
+        from .sd_blocks import weight_generation
+        if self._graph_gen != weight_generation():
+            self._graphs, self._graph_gen = {}, weight_generation()
+        key = (tuple(images.shape), task, noise is not None, str(images.device), bool(quantize))
         g = self._graphs.get(key)
         if g is None:
-            g = self._graphs[key] = _GraphedForward(self, images, task, noise)
+            g = self._graphs[key] = _GraphedForward(self, images, task, noise, quantize)
         return g(images, noise)
 
-    def _forward_impl(self, images, task, noise=None):
+    def _forward_impl(self, images, task, noise=None, quantize=False):
         org_h, org_w = images.shape[-2:]
         h, w = org_h, org_w
         images = images.float()
@@ -227,32 +220,44 @@ class DiffUIE(nn.Module):
         n_post, n_diff = noise if noise is not None else (None, None)
         z0, z0_8, mids = self.ae.run_encode(images, enable_fr=self.fr_type is not None, noise=n_post)
         zt = self.restore_latents(z0, z0_8, n_diff) if self.control_type else z0
-        preds = self.ae.run_decode(zt, mids, task, crop_hw=(h, w))               # unifie.py:155,164
-        if (h, w) != (org_h, org_w):                                             # unifie.py:165-168
-            preds = ops.resize_pad(preds, (org_h, org_w))
+        back = (h, w) != (org_h, org_w)
+        preds = self.ae.run_decode(zt, mids, task, crop_hw=(h, w), quantize=quantize and not back)   # unifie.py:155,164
+        if back:                                                                 # unifie.py:165-168
+            preds = ops.resize_pad(preds, (org_h, org_w), quantize=quantize)
         return preds
+
+
+def center_crop(image, upper=(512, 512)):
+    """``crop_tensor`` of the validate loop (eval_image_restoration.py:113-134): centre crop to at most ``upper`` as a
+    strided VIEW -- ``DiffUIE.forward`` reads it in place (``ur_image_to_nhwc8`` / ``ur_resize_pad`` take strides)."""
+    if image.ndim not in (3, 4):
+        raise NotImplementedError
+    h, w = image.shape[-2:]
+    ch, cw = min(h, upper[0]), min(w, upper[1])
+    return image[..., h // 2 - ch // 2: h // 2 + ch // 2, w // 2 - cw // 2: w // 2 + cw // 2]
 
 
 class _GraphedForward:
     """One captured CUDA graph of ``DiffUIE._forward_impl`` for fixed input shapes; inputs are copied into static
     buffers, the graph is replayed, the static output is cloned."""
 
-    def __init__(self, model, images, task, noise):
+    def __init__(self, model, images, task, noise, quantize=False):
         self.img = images.detach().float().clone()
         self.noise = tuple(n.detach().float().clone() for n in noise) if noise is not None else None
         side = torch.cuda.Stream(device=images.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                    # warm-up: weight packing, caches, function attributes
             for _ in range(2):
-                model._forward_impl(self.img, task, self.noise)
+                model._forward_impl(self.img, task, self.noise, quantize)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from .. import _cabi
-        n0 = _cabi.launch_count
+        n0, by0 = _cabi.launch_count, dict(_cabi.launch_counts)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = model._forward_impl(self.img, task, self.noise)
+            self.out = model._forward_impl(self.img, task, self.noise, quantize)
         self.n_launches = _cabi.launch_count - n0          # C-ABI kernel launches recorded in the graph
+        self.launches_by_entry = {k: v - by0.get(k, 0) for k, v in _cabi.launch_counts.items() if v - by0.get(k, 0)}
 
     def __call__(self, images, noise):
         self.img.copy_(images, non_blocking=True)

@@ -45,7 +45,8 @@ class SKPSNR(_ImageMetric):
         acc = 0.0
         for s, C, H, W in self._sums:
             for se in s[:, 0].tolist():
-                acc += 10.0 * math.log10(self.data_range ** 2 / (se / (C * H * W)))
+                # identical images (mse == 0): skimage's peak_signal_noise_ratio returns inf (division by zero warning)
+                acc += 10.0 * math.log10(self.data_range ** 2 / (se / (C * H * W))) if se > 0.0 else float("inf")
         return acc / max(self.total, 1)
 
 

@@ -22,7 +22,29 @@ TAPS_3x3_NOPAD = tuple((ky, kx) for ky in range(3) for kx in range(3))          
 
 
 def _stream():
+    """The current stream of the CURRENT device; every public op runs under ``_on_device`` which makes the device of
+    its first tensor argument current, so a model on cuda:1 never launches on cuda:0's stream."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device(fn):
+    """Run ``fn`` with the device of its first CUDA tensor argument current (a no-op compare on the common path)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        for t in args:
+            if isinstance(t, torch.Tensor):
+                if t.is_cuda:
+                    idx = t.device.index
+                    if idx not in _cabi._inited:
+                        _cabi.ensure_init(idx)
+                    if idx != torch.cuda.current_device():
+                        with torch.cuda.device(idx):
+                            return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+    return wrapped
 
 
 def _ptr(t):
@@ -52,15 +74,30 @@ def _check_nhwc(t, name):
     return ld
 
 
-_ABLATE = set(filter(None, os.environ.get("UR_ABLATE", "").split(",")))   # development: time-share ablations
 _WS = {}
 _ROLE = ["main"]      # which execution context issues the calls: "main" or "ctl" (the Controller's side stream)
+_WS_ROLE = [None]     # workspace owner when it differs from the statistics-pool role (the SC-Tuner side stream)
 
 
-def _workspace(device, nbytes=16 << 20):
+class workspace_role:
+    """``with workspace_role("sct"):`` -- kernels issued inside use their own split-K workspace.  Every stream that can
+    run concurrently with another one owns a workspace (Controller: role "ctl" via stats_arena_begin; SC-Tuner: "sct")."""
+
+    def __init__(self, name):
+        self.name, self.prev = name, None
+
+    def __enter__(self):
+        self.prev, _WS_ROLE[0] = _WS_ROLE[0], self.name
+
+    def __exit__(self, *a):
+        _WS_ROLE[0] = self.prev
+
+
+def _workspace(device, nbytes=32 << 20):
     """Caller-owned split-K scratch handed to every ur_conv_gemm call: one per (device, role), since the Controller
-    of the next DDIM step runs on a side stream concurrently with the UNet (stream-ordered reuse within a stream)."""
-    key = (device, _ROLE[0])
+    of the next DDIM step and the SC-Tuner adapters run on side streams concurrently with the UNet (stream-ordered
+    reuse within a stream)."""
+    key = (device, _WS_ROLE[0] or _ROLE[0])
     ws = _WS.get(key)
     if ws is None:
         ws = _WS[key] = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
@@ -88,7 +125,7 @@ def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None
         if x2.shape[:3] != x.shape[:3]:
             raise ValueError("x2 spatial shape mismatch")
         if C1 % 64:      # the two-source TMA path needs 64-aligned source-1 channels: materialise the concat
-            x, x2 = torch.cat([x, x2], dim=-1), None
+            x, x2 = concat_channels(x, x2), None
             C1, ld1 = x.shape[3], x.shape[3]
         else:
             C2, ld2 = x2.shape[3], _check_nhwc(x2, "x2")
@@ -141,14 +178,13 @@ def conv_gemm(x, w, n, *, x2=None, taps=TAPS_1x1, stride=1, hout=None, wout=None
         d.residual = r.data_ptr()
         d.res_sb, d.res_sy, d.res_sx = r.stride(0), r.stride(1), r.stride(2)
     d.act, d.bn = act, bn
-    if (want_stats or stats is not None) and out.dtype == torch.bfloat16 and "nofusedstats" not in _ABLATE:
+    if (want_stats or stats is not None) and out.dtype == torch.bfloat16:
         if stats is None:
             stats = new_stats(x.device, B, n_out)
         d.stats, d.stats_ld, d.stats_off = stats.data_ptr(), n_out, 0
         ret._ur_stats = stats
     ws = _workspace(x.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
-    _cabi.ensure_init(x.device.index or 0)
     check(_cabi.lib().ur_conv_gemm(C.byref(d), _stream()), "ur_conv_gemm")
     return ret
 
@@ -230,7 +266,8 @@ def stats_arena_begin(device, role="main", capacity=32 << 20):
 
 def stats_arena_end(device):
     a = _arena_for(device)
-    a.hwm, a.active = max(a.hwm, a.off), False
+    # the mark never exceeds the pool: requests past the end of the pool keep taking fresh buffers on every pass
+    a.hwm, a.active = min(max(a.hwm, a.off), a.buf.numel()), False
     _ROLE[0] = "main"
 
 
@@ -238,7 +275,7 @@ def new_stats(device, B, channels):
     """Zeroed fp64 ``[B, channels, 2]`` statistics buffer: from the per-step pool when one is active, else a fresh fill."""
     a, n = _arena_for(device), B * channels * 2
     if a.active:
-        if a.off + n <= (a.hwm if a.hwm else a.buf.numel()):
+        if a.off + n <= min(a.hwm if a.hwm else a.buf.numel(), a.buf.numel()):
             st = a.buf[a.off:a.off + n].view(B, channels, 2)
             a.off += n
             return st
@@ -253,7 +290,7 @@ def chan_stats(x, stats=None, offset=0, total_channels=None, zero=True):
     if stats is None:
         a, n = _arena_for(x.device), B * total * 2
         # the zeroed prefix is [0, hwm) (the whole pool on the first pass)
-        if a.active and a.off + n <= (a.hwm if a.hwm else a.buf.numel()):
+        if a.active and a.off + n <= min(a.hwm if a.hwm else a.buf.numel(), a.buf.numel()):
             stats, zero = a.buf[a.off:a.off + n].view(B, total, 2), False
             a.off += n
         else:
@@ -297,11 +334,6 @@ def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
     of the cluster kernel ``ur_group_norm`` (statistics in distributed shared memory) instead."""
     B, P, C1, ld1, is1 = _geom(x)
     C2 = x2.shape[-1] if x2 is not None else 0
-    if "gn" in _ABLATE and B * P * (C1 + C2) * 2 <= (96 << 20):
-        return x if x2 is None else torch.empty(tuple(x.shape[:-1]) + (C1 + C2,), device=x.device, dtype=x.dtype)
-    if "gnstats" in _ABLATE and B * P * (C1 + C2) * 2 <= (96 << 20):
-        st = torch.zeros((B, C1 + C2, 2), device=x.device, dtype=torch.float64) + 1.0
-        return norm_apply(x, st, groups, gamma, beta, eps, silu, x2)
     if B * P * (C1 + C2) * 2 <= FUSED_GN_MAX_BYTES and (C1 + C2) <= 8192:
         ld2, is2 = 0, 0
         if x2 is not None:
@@ -328,8 +360,6 @@ def group_norm(x, groups, gamma, beta, eps, silu=False, x2=None):
 
 
 def layernorm(x, gamma, beta, eps):
-    if "ln" in _ABLATE:
-        return x
     B, P, Cc, ld, ist = _geom(x)
     if B > 1 and ist != P * ld:
         raise ValueError("layernorm needs a dense token matrix")
@@ -372,8 +402,6 @@ def attention(q, k, v, heads, out=None):
     512-wide head) take the unfused GEMM -> softmax -> GEMM path."""
     B, Tq, Cc = q.shape
     d = Cc // heads
-    if "attn" in _ABLATE and d in (64, 128):
-        return q if q.is_contiguous() else q.contiguous()
     if d not in (64, 128):
         return attention_unfused(q, k, v, heads, out)
     Tk = k.shape[1]
@@ -510,17 +538,33 @@ def image_to_nhwc8(img, a=1.0, b=0.0):
     return out
 
 
-def nhwc_to_image(src, channels, h=None, w=None, a=1.0, b=0.0):
-    """fp32 channels-last [B,Hs,Ws,ld] -> fp32 NCHW [B,channels,h,w] = a*src+b (top-left crop)."""
+def nhwc_to_image(src, channels, h=None, w=None, a=1.0, b=0.0, y0=0, x0=0, quantize=False):
+    """fp32 channels-last [B,Hs,Ws,ld] -> fp32 NCHW [B,channels,h,w] = a*src[:, y0:y0+h, x0:x0+w]+b;
+    ``quantize``: the 8-bit quantisation of eval_image_restoration.py:71 fused into the write-out."""
     B, Hs, Ws, ld = src.shape
-    h, w = h or Hs, w or Ws
+    h, w = h or Hs - y0, w or Ws - x0
     out = torch.empty((B, channels, h, w), device=src.device, dtype=torch.float32)
-    check(_lib().ur_nhwc_to_image(_f32(src, "src"), ld, Hs, Ws, B, channels, h, w, a, b, _ptr(out), _stream()),
-          "ur_nhwc_to_image")
+    check(_lib().ur_nhwc_to_image(_f32(src, "src"), ld, Hs, Ws, B, channels, h, w, y0, x0, a, b, int(quantize), _ptr(out),
+                                  _stream()), "ur_nhwc_to_image")
     return out
 
 
-def resize_pad(img, size=None, pad_bottom=0, pad_right=0):
+def concat_channels(x1, x2):
+    """Dense bf16 ``cat(x1, x2)`` along channels (one copy kernel; channel-slice views accepted as sources)."""
+    x1, x2 = _as4(x1), _as4(x2)
+    ld1, ld2 = _check_nhwc(x1, "x1"), _check_nhwc(x2, "x2")
+    B, H, W, C1 = x1.shape
+    C2 = x2.shape[3]
+    for t, ld in ((x1, ld1), (x2, ld2)):
+        if B > 1 and t.stride(0) != H * W * ld:
+            raise ValueError("concat_channels needs a uniform pixel pitch")
+    out = torch.empty((B, H, W, C1 + C2), device=x1.device, dtype=torch.bfloat16)
+    check(_lib().ur_concat_channels(_ptr(x1), ld1, C1, _ptr(x2), ld2, C2, B * H * W, _ptr(out), _stream()),
+          "ur_concat_channels")
+    return out
+
+
+def resize_pad(img, size=None, pad_bottom=0, pad_right=0, quantize=False):
     """``F.pad(F.interpolate(img, size, mode="bicubic", align_corners=False), (0, pad_right, 0, pad_bottom), "reflect")``
     on a CUDA fp32 NCHW image in one kernel (unifie.py:124-134,165-168); ``size=None`` keeps the resolution."""
     if img.dtype != torch.float32 or not img.is_cuda or img.dim() != 4:
@@ -529,5 +573,14 @@ def resize_pad(img, size=None, pad_bottom=0, pad_right=0):
     hr, wr = (H, W) if size is None else (int(size[0]), int(size[1]))
     out = torch.empty((B, Cc, hr + pad_bottom, wr + pad_right), device=img.device, dtype=torch.float32)
     check(_lib().ur_resize_pad(_ptr(img), img.stride(0), img.stride(1), img.stride(2), img.stride(3), B, Cc, H, W, hr, wr,
-                               pad_bottom, pad_right, _ptr(out), _stream()), "ur_resize_pad")
+                               pad_bottom, pad_right, int(quantize), _ptr(out), _stream()), "ur_resize_pad")
     return out
+
+
+# every op that launches kernels runs with its first tensor argument's device current (and the library initialised)
+for _name in ("conv_gemm", "chan_stats", "norm_apply", "group_norm", "layernorm", "scale_channels_", "softmax_rows",
+              "transpose_tokens", "attention", "dwconv3x3_gate", "small_linear", "timestep_embedding", "adanaf_scales",
+              "tfa_gates", "posterior_sample", "latent_axpby", "ddim_step_", "image_to_nhwc8", "nhwc_to_image",
+              "resize_pad", "concat_channels"):
+    globals()[_name] = _on_device(globals()[_name])
+del _name
