@@ -270,6 +270,7 @@ def torch_eager_same_gpu(a, dev, img):
     from oracle import unirestore as O
     cfg = (CFG[0], dict(CFG[1], num_inference_steps=a.ddim_steps), CFG[2])
     om = cheap_init_(O.DiffUIE(*cfg)).eval().requires_grad_(False).to(dev)
+    om.scheduler.set_timesteps(a.ddim_steps, device=dev)            # as Lightning would (unifie.py:73-75)
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         for _ in range(2):
             om(img, a.task)

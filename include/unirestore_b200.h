@@ -111,6 +111,10 @@ int ur_debug_set_gemm_splitk(int on);
 /* Development: 0 = persistent-kernel epilogue stores with st.global instead of TMA; returns the previous value. */
 int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
+/* Development: attention kernel generation for head_dim 64 / 128: 2 = attention2_kernel (default: one softmax thread per
+ * row, two query tiles per CTA, single TMEM pass, exp2 partly on the FMA pipe), 1 = first-generation kernel; returns the
+ * previous value. */
+int ur_debug_set_attention_impl(int impl);
 
 /* ------------------------------------------------------------------------------------------------
  * Normalisation (HBM-bound, bf16 channels-last, 128-bit vectorised)

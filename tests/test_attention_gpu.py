@@ -24,10 +24,21 @@ def _ref(q, k, v, heads):
     return bf16_round(o.transpose(1, 2).reshape(B, Tq, C))
 
 
+@pytest.fixture(params=[2, 1], ids=["attention2", "attention1"])
+def impl(request):
+    """Both kernel generations: attention2_kernel (default) and the first-generation attention_kernel kept for A/B."""
+    from unirestore_b200 import _cabi
+    old = _cabi.lib().ur_debug_set_attention_impl(request.param)
+    yield request.param
+    _cabi.lib().ur_debug_set_attention_impl(old)
+
+
 @pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 5, 64, 256, 256), (1, 2, 64, 128, 128), (2, 4, 64, 200, 300),
                                              (1, 5, 64, 4096, 4096), (2, 4, 128, 64, 64), (3, 4, 128, 256, 256),
-                                             (2, 20, 64, 4, 4), (1, 10, 64, 1024, 1024), (2, 1, 64, 130, 7)])
-def test_fused_self_attention_packed_qkv(B, heads, d, Tq, Tk):
+                                             (2, 20, 64, 4, 4), (1, 10, 64, 1024, 1024), (2, 1, 64, 130, 7),
+                                             (1, 3, 64, 384, 1000), (2, 2, 64, 129, 129), (1, 2, 128, 300, 200),
+                                             (1, 1, 64, 256, 33)])
+def test_fused_self_attention_packed_qkv(impl, B, heads, d, Tq, Tk):
     from unirestore_b200 import ops
     torch.backends.cuda.matmul.allow_tf32 = False
     C = heads * d
@@ -41,7 +52,7 @@ def test_fused_self_attention_packed_qkv(B, heads, d, Tq, Tk):
 
 
 @pytest.mark.parametrize("B,heads,Tq", [(4, 5, 4096), (2, 10, 1024), (3, 20, 64)])
-def test_fused_cross_attention_shared_kv(B, heads, Tq):
+def test_fused_cross_attention_shared_kv(impl, B, heads, Tq):
     """K/V of the constant 77-token null prompt shared by all images (base_model.py:221)."""
     from unirestore_b200 import ops
     C = heads * 64
@@ -59,3 +70,24 @@ def test_unfused_attention(B, heads, d, Tq, Tk):
     q, k, v = _rand(B, Tq, C, seed=7), _rand(B, Tk, C, seed=8), _rand(B, Tk, C, seed=9)
     y = ops.attention_unfused(q, k, v, heads)
     assert_close(y, _ref(q, k, v, heads), 3e-3, "unfused attention %s" % ((B, heads, d, Tq, Tk),))
+
+
+def test_attention_large_score_range_lazy_rescale():
+    """Scores whose running maximum grows by far more than 2^8 from KV tile to KV tile (the lazy-rescaling path of both
+    kernels: O and l are rescaled in TMEM) and rows dominated by a single key."""
+    from unirestore_b200 import _cabi, ops
+    B, heads, d, T = 1, 2, 64, 1024
+    g = torch.Generator().manual_seed(21)
+    q = torch.randn(B, T, heads * d, generator=g) * 3.0
+    k = torch.randn(B, T, heads * d, generator=g)
+    k = k * torch.linspace(0.2, 6.0, T).view(1, T, 1)                 # later keys score much higher / lower
+    v = torch.randn(B, T, heads * d, generator=g)
+    q, k, v = (t.to(DEV).to(torch.bfloat16) for t in (q, k, v))
+    ref = _ref(q, k, v, heads)
+    for impl in (2, 1):
+        old = _cabi.lib().ur_debug_set_attention_impl(impl)
+        try:
+            y = ops.attention(q, k, v, heads)
+        finally:
+            _cabi.lib().ur_debug_set_attention_impl(old)
+        assert_close(y, ref, 4e-3, "flash attention impl %d, growing score range" % impl)

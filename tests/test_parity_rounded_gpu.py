@@ -97,7 +97,7 @@ def test_transformer2d(c, heads, hw):
     ctx = bq(rnd(7, 1, 77, 1024)).to(DEV)
     y = m.run(nhwc(x), ctx.to(torch.bfloat16).contiguous())
     check(nchw(y), R.transformer2d(o, x, ctx.expand(2, -1, -1)), o(x, ctx.expand(2, -1, -1), return_dict=False)[0],
-          "Transformer2DModel c=%d @%dx%d" % (c, *hw))
+          "Transformer2DModel c=%d @%dx%d" % (c, *hw), tol=4e-3)       # ~15 rounding points in series
 
 
 def test_scedit_cfrm_tfa():
