@@ -89,7 +89,7 @@ def _heads(t, h):
 
 
 # head dims served by the fused flash kernel (ur_attention); others take GEMM -> ur_softmax_rows -> GEMM
-FLASH_HEAD_DIMS = {64, 128}
+FLASH_HEAD_DIMS = {64, 128, 512}
 
 
 def _fused_attention(dim_head):

@@ -63,6 +63,23 @@ def test_fused_cross_attention_shared_kv(impl, B, heads, Tq):
     assert_close(y, _ref(q, k, v, heads), 3e-3, "flash cross attention %s" % ((B, heads, Tq),))
 
 
+@pytest.mark.parametrize("B,heads,Tq,Tk", [(2, 1, 96, 96), (1, 1, 1024, 1024), (2, 1, 4096, 4096), (1, 2, 300, 200),
+                                           (1, 1, 16384, 16384)])
+def test_fused_attention_head_dim_512(B, heads, Tq, Tk):
+    """attention512_kernel: the VAE mid-block head (autoencoder.py:32,44) at 512^2 (4 096 tokens) and 1024^2 (16 384
+    tokens) latents, ragged token counts and two heads; no score tensor in HBM."""
+    from unirestore_b200 import ops
+    C = heads * 512
+    qkv = _rand(B, max(Tq, Tk), 3 * C, seed=12)
+    q, k, v = qkv[:, :Tq, :C], qkv[:, :Tk, C:2 * C], qkv[:, :Tk, 2 * C:]
+    y = ops.attention(q, k, v, heads)
+    if Tq * Tk > 1 << 26:                      # 16 384^2: check a slice of the queries against the fp32 reference
+        idx = torch.arange(0, Tq, 61, device=DEV)
+        assert_close(y[:, idx], _ref(q[:, idx], k, v, heads), 3e-3, "flash attention d=512 %s (query slice)" % ((B, heads, Tq, Tk),))
+    else:
+        assert_close(y, _ref(q, k, v, heads), 3e-3, "flash attention d=512 %s" % ((B, heads, Tq, Tk),))
+
+
 @pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 1, 512, 96, 96), (1, 1, 512, 1024, 1024), (2, 5, 64, 64, 77)])
 def test_unfused_attention(B, heads, d, Tq, Tk):
     from unirestore_b200 import ops

@@ -251,6 +251,8 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
           l *= alpha;
         }
         if (need) m = mx;
+      } else if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);      // P_{j-1} V_{j-1} has consumed the P buffer this tile overwrites
       }
       if (trs) p.trace[(j - 4) * 8 + 4] = clock64();
       // ---- pass 2: P = exp2(s * scale - max) -> bf16 -> shared memory (K-major SW128), partial row sum
@@ -718,6 +720,302 @@ static int launch_attention2(const AttnParams& p, const CUtensorMap& mq, const C
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention2 launch");
 }
 
+// One softmax thread's whole KV loop (shared by attention512_kernel; same arithmetic as the softmax branch of
+// attention2_kernel): tS / tO = TMEM addresses of this thread's S row (128 columns) and O row (OW columns), prow = its
+// row of the P tile in shared memory (two K-major SW128 blocks 128 x 64), swz = row & 7.
+template <int OW>
+__device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint8_t* prow, uint32_t swz, uint64_t* s_full,
+                                             uint64_t* s_empty, uint64_t* p_full, uint64_t* o_full, int nkv, int Tk,
+                                             float sc, bf16* op, bool row_valid) {
+  float m = -INFINITY, mrun = -INFINITY, l0 = 0.f, l1 = 0.f;
+  for (int j = 0; j < nkv; ++j) {
+    const int kvalid = Tk - j * kTileK;
+    const int nchunk = kvalid >= kTileK ? 4 : ((kvalid + 31) >> 5);
+    mbar_wait(s_full, j & 1);
+    tc_fence_after();
+    uint32_t v[4][32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < nchunk) tmem_ld32(tS + c * 32, v[c]);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(s_empty);
+    if (kvalid < kTileK) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i >= kvalid && c < nchunk) v[c][i] = __float_as_uint(-INFINITY);
+    }
+    float mx0 = mrun, mx1 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nchunk) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = max3(mx0, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
+          mx1 = max3(mx1, __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
+        }
+      }
+    }
+    mrun = fmaxf(mx0, mx1);
+    const float mxl = mrun * sc;
+    const bool need = (j == 0) || (mxl - m > 8.0f);
+    if (__any_sync(0xffffffffu, need)) {
+      const float alpha = need ? exp2_approx(m - mxl) : 1.0f;
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < OW / 32; ++c) {
+          uint32_t t0[32];
+          tmem_ld32(tO + c * 32, t0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * alpha);
+          tmem_st32(tO + c * 32, t0);
+        }
+        tmem_st_wait();
+        l0 *= alpha;
+        l1 *= alpha;
+      }
+      if (need) m = mxl;
+    } else if (j > 0) {
+      mbar_wait(o_full, (j - 1) & 1);
+    }
+    const float nm = -m;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < nchunk) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a0, a1, e0, e1;
+          fma2(a0, a1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sc, nm);
+          if ((i & 7) < kPolyOf8) {
+            exp2_poly2(e0, e1, a0, a1);
+          } else {
+            e0 = exp2_approx(a0);
+            e1 = exp2_approx(a1);
+          }
+          add2(l0, l1, l0, l1, e0, e1);
+          pk[i] = pack_bf16(e0, e1);
+        }
+        uint8_t* pblk = prow + (c >> 1) * (kTileQ * 128);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
+          *reinterpret_cast<uint4*>(pblk + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    mbar_arrive(p_full);
+  }
+  mbar_wait(o_full, (nkv - 1) & 1);
+  tc_fence_after();
+  const float inv = 1.f / (l0 + l1);
+#pragma unroll
+  for (int c = 0; c < OW / 32; ++c) {
+    uint32_t t0[32];
+    tmem_ld32(tO + c * 32, t0);
+    tmem_ld_wait();
+    if (row_valid) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(t0[8 * i]) * inv, __uint_as_float(t0[8 * i + 1]) * inv);
+        o.y = pack_bf16(__uint_as_float(t0[8 * i + 2]) * inv, __uint_as_float(t0[8 * i + 3]) * inv);
+        o.z = pack_bf16(__uint_as_float(t0[8 * i + 4]) * inv, __uint_as_float(t0[8 * i + 5]) * inv);
+        o.w = pack_bf16(__uint_as_float(t0[8 * i + 6]) * inv, __uint_as_float(t0[8 * i + 7]) * inv);
+        reinterpret_cast<uint4*>(op + c * 32)[i] = o;
+      }
+    }
+  }
+}
+
+// =====================================================================================================================
+// attention512_kernel: flash attention for ONE 512-wide head (the VAE mid-block Attention of autoencoder.py:32,44:
+// diffusers Attention(512, heads=1, dim_head=512) over all 4 096 / 16 384 latent pixels).  Replaces the GEMM -> fp32
+// scores -> softmax -> GEMM path: no score tensor in HBM (4 096^2 fp32 = 64 MB per image, 16 384^2 = 1 GB).
+//
+//   O[128 x 512] fp32 would need all 512 TMEM columns, leaving none for S: the output columns are split in two halves
+//   and a CTA owns (128-query tile, column half, image); both halves compute S = Q K^T (1.5x the minimal FLOPs, the
+//   price of keeping S and O on chip).  TMEM: S 128 + O 256 columns.
+//   Q (128 x 512, 128 KB) stays resident in shared memory; K_j streams through a 4-stage ring as eight 64-channel
+//   chunks (S accumulates over them), V_j as four 64-column chunks of this CTA's half, all 16 KB boxes:
+//     warp 0 TMA producer   K(0); then per KV tile j:  K(j+1) chunks, V(j) chunks      (the MMA warp's consumption order)
+//     warp 1 tcgen05 issuer S(0); then per j: [s_empty(j)] S(j+1);  [p_full(j)] O += P(j) V(j)
+//     warps 4..7 softmax, one thread per query row -- same single-pass arithmetic as attention2_kernel.
+//   The main loop is tensor-bound (3 072 tensor cycles per KV tile against ~700 softmax cycles).
+// =====================================================================================================================
+constexpr int kD5 = 512, kOW5 = 256, kRing5 = 4, kChunk5 = kTileK * 64 * 2;     // 16 KB ring stages
+
+__global__ void __launch_bounds__(256, 1)
+attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
+                    const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
+  constexpr int kQBytes = kTileQ * kD5 * 2;             // 128 KB: 8 blocks of [128 rows x 128 B]
+  constexpr int kPBytes = kTileQ * kTileK * 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sR = sQ + kQBytes;                           // ring: kRing5 x 16 KB
+  uint8_t* sP = sR + kRing5 * kChunk5;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* q_full = bars;
+  uint64_t* r_full = q_full + 1;                        // [kRing5]
+  uint64_t* r_empty = r_full + kRing5;                  // [kRing5]
+  uint64_t* s_full = r_empty + kRing5;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTileQ;
+  const int h = blockIdx.y >> 1, half = blockIdx.y & 1;
+  const int b = blockIdx.z;
+  const int nkv = (p.Tk + kTileK - 1) / kTileK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kRing5; ++s) {
+      mbar_init(&r_full[s], 1);
+      mbar_init(&r_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one_sync()) {
+      mbar_expect_tx(q_full, kQBytes);
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) tma_load_3d(sQ + nb * (kTileQ * 128), &mapQ, q_full, h * kD5 + nb * 64, q0, b);
+    }
+    __syncwarp();
+    const int bk = p.kv_shared ? 0 : b;
+    int it = 0;
+    auto load = [&](const CUtensorMap* m, int ch, int j) {
+      const int s = it % kRing5;
+      mbar_wait(&r_empty[s], ((it / kRing5) & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&r_full[s], kChunk5);
+        tma_load_3d(sR + s * kChunk5, m, &r_full[s], ch, j * kTileK, bk);
+      }
+      __syncwarp();
+      ++it;
+    };
+    for (int c = 0; c < 8; ++c) load(&mapK, h * kD5 + c * 64, 0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv)
+        for (int c = 0; c < 8; ++c) load(&mapK, h * kD5 + c * 64, j + 1);
+      for (int c = 0; c < 4; ++c) load(&mapV, h * kD5 + half * kOW5 + c * 64, j);
+    }
+   } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V chunk) is MN-major
+    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aR = smem_u32(sR);
+    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+    int it = 0;
+    mbar_wait(q_full, 0);
+    auto issue_s = [&]() {                    // S = sum over eight 64-channel chunks of Q_c K_c^T
+      for (int c = 0; c < 8; ++c, ++it) {
+        const int s = it % kRing5;
+        mbar_wait(&r_full[s], (it / kRing5) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tS, umma_desc_k_sw128(aQ + c * (kTileQ * 128)) + 2 * k, umma_desc_k_sw128(aR + s * kChunk5) + 2 * k,
+                        idesc_s, (c | k) != 0 ? 1u : 0u);
+          tc_commit(&r_empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one_sync()) tc_commit(s_full);
+      __syncwarp();
+    };
+    issue_s();
+    for (int j = 0; j < nkv; ++j) {
+      const int kvalid = min(kTileK, p.Tk - j * kTileK);
+      const int nk16 = ((kvalid + 31) >> 5) << 1;
+      mbar_wait(s_empty, j & 1);              // the softmax threads hold S(j) in registers
+      if (j + 1 < nkv) issue_s();             // S(j+1) runs under the softmax of tile j
+      mbar_wait(p_full, j & 1);
+      for (int c = 0; c < 4; ++c, ++it) {     // O[:, 64 c .. 64 c + 64) += P(j) V_c(j)
+        const int s = it % kRing5;
+        mbar_wait(&r_full[s], (it / kRing5) & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          for (int k = 0; k < nk16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(aP + (k >> 2) * (kTileQ * 128)) + 2 * (k & 3);
+            const uint64_t db = umma_desc_mn_sw128(aR + s * kChunk5 + k * 16 * 128, kTileK * 128);
+            tc_mma_bf16(tO + c * 64, da, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&r_empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one_sync()) tc_commit(o_full);
+      __syncwarp();
+    }
+   }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // =============================== softmax / output: one thread per query row ===============================
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const int q = q0 + r;
+    softmax_rows<kOW5>(tmem_base + lane_off, tmem_base + lane_off + 128, sP + r * 128, static_cast<uint32_t>(r & 7),
+                       s_full, s_empty, p_full, o_full, nkv, p.Tk, p.scale_log2,
+                       p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * kD5 + half * kOW5, q < p.Tq);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int launch_attention512(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                               cudaStream_t stream) {
+  constexpr int smem = kTileQ * kD5 * 2 + kRing5 * kChunk5 + kTileQ * kTileK * 2 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention512)");
+    configured = true;
+  }
+  dim3 grid((p.Tq + kTileQ - 1) / kTileQ, 2 * p.heads, p.batch);
+  cudaError_t e = launch_kernel(attention512_kernel, grid, dim3(256), smem, stream, p, mq, mk, mv);
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention512 launch");
+}
+
 template <int D>
 static int launch_attention(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                             dim3 grid, cudaStream_t stream) {
@@ -745,7 +1043,7 @@ static int make_qkv_map(CUtensorMap* m, const void* ptr, int width, int64_t ld, 
 using namespace ur;
 
 static long long* g_attn_trace = nullptr;
-static int g_attn_impl = 2;      // 2: attention2_kernel (default); 1: first-generation attention_kernel (kept for A/B)
+static int g_attn_impl = 1;      // 1: attention_kernel (default: measured faster, r2c2); 2: attention2_kernel
 // development: select the attention kernel generation (returns the previous one)
 extern "C" int ur_debug_set_attention_impl(int impl) {
   const int old = g_attn_impl;
@@ -763,7 +1061,8 @@ extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void
                             int heads, int head_dim, int tq, int tk, int kv_shared, float scale, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (!q || !k || !v || !out) return set_error(UR_ERR_ARG, "ur_attention: null pointer");
-  if (head_dim != 64 && head_dim != 128) return set_error(UR_ERR_ARG, "ur_attention: head_dim must be 64 or 128");
+  if (head_dim != 64 && head_dim != 128 && head_dim != 512)
+    return set_error(UR_ERR_ARG, "ur_attention: head_dim must be 64, 128 or 512");
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_bs % 8 || k_bs % 8 || v_bs % 8 || out_bs % 8 ||
       ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
         reinterpret_cast<uintptr_t>(out)) & 15))
@@ -789,6 +1088,7 @@ extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void
   p.ldo = ldo;
   p.out_bs = out_bs;
   p.trace = g_attn_trace;
+  if (head_dim == 512) return launch_attention512(p, mq, mk, mv, stream);
   if (g_attn_impl == 2)
     return head_dim == 64 ? launch_attention2<64, 2>(p, mq, mk, mv, stream) : launch_attention2<128, 1>(p, mq, mk, mv, stream);
   dim3 grid((tq + kTileQ - 1) / kTileQ, heads, batch);

@@ -416,8 +416,11 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
   w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
 }
 // pred.mul(255).round_().clamp_(0, 255).div_(255) of the validate loop (eval_image_restoration.py:71); rintf rounds
-// half to even like torch.round
-__device__ __forceinline__ float quantize8(float v) { return fminf(fmaxf(rintf(v * 255.0f), 0.0f), 255.0f) / 255.0f; }
+// half to even like torch.round; PyTorch's CUDA kernels divide by a scalar as a multiplication by its fp32 reciprocal,
+// which is what the reference computes on its GPUs -- mirrored so the result is bit-identical to that expression
+__device__ __forceinline__ float quantize8(float v) {
+  return fminf(fmaxf(rintf(v * 255.0f), 0.0f), 255.0f) * (1.0f / 255.0f);
+}
 
 __global__ void resize_pad_kernel(const float* __restrict__ img, long long sb, long long sc, long long sy, long long sx,
                                   int C, int Hin, int Win, int Hr, int Wr, int Ho, int Wo, float scale_y, float scale_x,

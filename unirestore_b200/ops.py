@@ -398,11 +398,11 @@ def transpose_tokens(x, tokens_pad=None):
 def attention(q, k, v, heads, out=None):
     """softmax(q k^T / sqrt(d)) v per head.  q [B,Tq,C], k/v [B or 1,Tk,C] bf16 (channel-slice views ok).
 
-    head_dim 64 / 128: one launch of the fused tcgen05 flash-attention kernel; other head dims (the VAE's single
-    512-wide head) take the unfused GEMM -> softmax -> GEMM path."""
+    head_dim 64 / 128 / 512 (the VAE's single 512-wide head): one launch of a fused tcgen05 flash-attention kernel;
+    other head dims (reduced test topologies only) take the unfused GEMM -> softmax -> GEMM path."""
     B, Tq, Cc = q.shape
     d = Cc // heads
-    if d not in (64, 128):
+    if d not in (64, 128, 512):
         return attention_unfused(q, k, v, heads, out)
     Tk = k.shape[1]
     shared = k.shape[0] == 1 and B > 1
