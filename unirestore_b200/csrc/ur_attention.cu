@@ -362,6 +362,11 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
 //     SM against 512 tensor cycles): scale / subtract and the row sum use packed fma.rn.f32x2 / add.rn.f32x2 (half the
 //     FMA-pipe instructions) and kPolyOf8 of every 8 element pairs take a degree-3 Cody-Waite polynomial exp2 on the
 //     FMA / ALU pipes instead of MUFU.EX2 (max relative error 7.5e-5, far below the bf16 rounding of P).
+//   * P never touches shared memory: the softmax threads write bf16 P straight into tensor memory (tcgen05.st) and
+//     P V runs with its A operand read from TMEM (tcgen05.mma [d], [a_tmem], b_desc).  With P in shared memory the kernel
+//     was bound by shared-memory bandwidth (measured slower than attention_kernel, gpurun_out/r2c2_bench_attn.log):
+//     32 KB of P stores + 32 KB of UMMA reads per 128 x 128 tile on top of 64 KB of Q / K / V operand reads at
+//     128 B/clk/SM.  TMEM: S 2 x 128 + O 2 x 64 + P 2 x 64 = 512 columns.
 //   * O accumulates in TMEM with the same exact lazy rescaling as attention_kernel (reference maximum only moves when
 //     the running maximum outgrew it by more than 2^8); the rescale touches the thread's own row only.
 //   warp 0 TMA (Q tiles once, 3-stage K/V ring), warp 1 tcgen05 issuer, warps 4.. softmax (one warp group per query
@@ -418,313 +423,13 @@ __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float
   y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-template <int D, int NQ>
-struct Attn2Cfg {
-  static constexpr int kStages = D == 64 ? 3 : 2;
-  static constexpr int kQBytes = kTileQ * D * 2;
-  static constexpr int kKBytes = kTileK * D * 2;
-  static constexpr int kPBytes = kTileQ * kTileK * 2;
-  static constexpr int kSmem = NQ * kQBytes + kStages * 2 * kKBytes + NQ * kPBytes + 1024;
-  static constexpr int kThreads = (4 + 4 * NQ) * 32;      // warp group 0: TMA, MMA, 2 idle warps; then 4 warps per query tile
-  static constexpr uint32_t kTmemCols = NQ * 128 + NQ * D <= 256 ? 256 : 512;
-};
-
-template <int D, int NQ>
-__global__ void __launch_bounds__(Attn2Cfg<D, NQ>::kThreads, 1)
-attention2_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
-                  const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
-  using Cfg = Attn2Cfg<D, NQ>;
-  constexpr int ND = D / 64;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kQBytes = Cfg::kQBytes, kKBytes = Cfg::kKBytes, kPBytes = Cfg::kPBytes;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;                                   // [NQ] x [ND blocks of 128 rows x 128 B]
-  uint8_t* sKV = sQ + NQ * kQBytes;                     // stage s: K at s * 2 * kKBytes, V right after
-  uint8_t* sP = sKV + kStages * 2 * kKBytes;            // [NQ] x [2 K-major blocks of 128 rows x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NQ * kPBytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = q_full + 1;                       // [kStages]
-  uint64_t* kv_empty = kv_full + kStages;               // [kStages]
-  uint64_t* s_full = kv_empty + kStages;                // [NQ]
-  uint64_t* s_empty = s_full + NQ;                      // [NQ]
-  uint64_t* p_full = s_empty + NQ;                      // [NQ]
-  uint64_t* o_full = p_full + NQ;                       // [NQ]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
-
-  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
-  const int q_base = blockIdx.x * (kTileQ * NQ);
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = (p.Tk + kTileK - 1) / kTileK;
-  const int nq_act = (NQ == 2 && q_base + kTileQ < p.Tq) ? 2 : 1;     // query tiles of this CTA that hold rows
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapK);
-    tma_prefetch_desc(&mapV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int x = 0; x < NQ; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&s_empty[x], 128);
-      mbar_init(&p_full[x], 128);
-      mbar_init(&o_full[x], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_launch_dependents();
-  pdl_wait();
-  // (each setmaxnreg sits inside its role's branch: after a control-flow merge ptxas would apply the smaller budget
-  //  to every role)
-  if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (elect_one_sync()) {
-      mbar_expect_tx(q_full, nq_act * kQBytes);
-      for (int x = 0; x < nq_act; ++x)
-#pragma unroll
-        for (int nb = 0; nb < ND; ++nb)
-          tma_load_3d(sQ + x * kQBytes + nb * (kTileQ * 128), &mapQ, q_full, h * D + nb * 64, q_base + x * kTileQ, b);
-    }
-    __syncwarp();
-    const int bk = p.kv_shared ? 0 : b;
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % kStages;
-      mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
-      uint8_t* sk = sKV + s * 2 * kKBytes;
-      if (elect_one_sync()) {
-        mbar_expect_tx(&kv_full[s], 2 * kKBytes);
-#pragma unroll
-        for (int nb = 0; nb < ND; ++nb) {
-          tma_load_3d(sk + nb * (kTileK * 128), &mapK, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
-          tma_load_3d(sk + kKBytes + nb * (kTileK * 128), &mapV, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
-        }
-      }
-      __syncwarp();
-    }
-   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
-    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aKV = smem_u32(sKV);
-    mbar_wait(q_full, 0);
-    auto issue_s = [&](int x, int j) {          // S_x(j) = Q_x K_j^T -> TMEM columns [128 x, 128 x + 128)
-      const int s = j % kStages;
-      if (x == 0) mbar_wait(&kv_full[s], (j / kStages) & 1);       // (x = 1 follows x = 0 of the same j)
-      tc_fence_after();
-      const uint32_t aK = aKV + s * 2 * kKBytes;
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int nb = 0; nb < ND; ++nb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_base + x * 128, umma_desc_k_sw128(aQ + x * kQBytes + nb * (kTileQ * 128)) + 2 * k,
-                        umma_desc_k_sw128(aK + nb * (kTileK * 128)) + 2 * k, idesc_s, (nb | k) != 0 ? 1u : 0u);
-        tc_commit(&s_full[x]);
-      }
-      __syncwarp();
-    };
-    for (int x = 0; x < nq_act; ++x) issue_s(x, 0);
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % kStages;
-      const uint32_t aV = aKV + s * 2 * kKBytes + kKBytes;
-      // k-steps of 16 keys that hold valid keys (the last KV tile may be partial; P columns past them are not written)
-      const int kvalid = min(kTileK, p.Tk - j * kTileK);
-      const int nk16 = ((kvalid + 31) >> 5) << 1;
-      for (int x = 0; x < nq_act; ++x) {
-        if (j + 1 < nkv) {
-          mbar_wait(&s_empty[x], j & 1);        // group x holds S_x(j) in registers
-          issue_s(x, j + 1);                    // runs under the softmax of tile j
-        }
-        mbar_wait(&p_full[x], j & 1);           // P_x(j) in shared memory, O_x rescaled if it had to be
-        tc_fence_after();
-        if (elect_one_sync()) {
-#pragma unroll
-          for (int nb = 0; nb < ND; ++nb) {
-            for (int k = 0; k < nk16; ++k) {
-              const uint64_t da = umma_desc_k_sw128(aP + x * kPBytes + (k >> 2) * (kTileQ * 128)) + 2 * (k & 3);
-              const uint64_t db = umma_desc_mn_sw128(aV + nb * (kTileK * 128) + k * 16 * 128, kTileK * 128);
-              tc_mma_bf16(tmem_base + NQ * 128 + x * D + nb * 64, da, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
-            }
-          }
-          tc_commit(&o_full[x]);
-          if (x == nq_act - 1) tc_commit(&kv_empty[s]);
-        }
-        __syncwarp();
-      }
-    }
-   }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    // =============================== softmax / output: one thread per query row ===============================
-    const int x = (warp - 4) >> 2;                       // query tile (softmax group)
-    const int qd = warp & 3;                             // TMEM lane quarter this warp may access
-    const int r = qd * 32 + lane;
-    if (x < nq_act) {
-      const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-      const uint32_t tS = tmem_base + lane_off + x * 128;
-      const uint32_t tO = tmem_base + lane_off + NQ * 128 + x * D;
-      uint8_t* prow = sP + x * kPBytes + r * 128;
-      const uint32_t swz = static_cast<uint32_t>(r & 7);
-      float m = -INFINITY;                               // reference maximum (log2 domain) of the exponentials
-      float mrun = -INFINITY;                            // running row maximum of the raw scores
-      float l0 = 0.f, l1 = 0.f;
-      const float sc = p.scale_log2;
-      for (int j = 0; j < nkv; ++j) {
-        const int kvalid = p.Tk - j * kTileK;
-        const int nchunk = kvalid >= kTileK ? 4 : ((kvalid + 31) >> 5);       // 32-column chunks holding valid keys
-        mbar_wait(&s_full[x], j & 1);
-        tc_fence_after();
-        uint32_t v[4][32];
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < nchunk) tmem_ld32(tS + c * 32, v[c]);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_empty[x]);                        // S_x(j) is in registers: S_x(j+1) may overwrite it
-        if (kvalid < kTileK) {                           // last tile: keys past Tk score -inf
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kvalid && c < nchunk) v[c][i] = __float_as_uint(-INFINITY);
-        }
-        // ---- row maximum (3-input max)
-        float mx0 = mrun, mx1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = max3(mx0, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
-              mx1 = max3(mx1, __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
-            }
-          }
-        }
-        mrun = fmaxf(mx0, mx1);
-        const float mxl = mrun * sc;                     // running maximum, log2 domain (scale > 0)
-        // ---- lazy rescaling of O / l (exact: softmax is shift invariant)
-        const bool need = (j == 0) || (mxl - m > 8.0f);
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? exp2_approx(m - mxl) : 1.0f;
-          if (j > 0) {
-            mbar_wait(&o_full[x], (j - 1) & 1);          // P(j-1) V(j-1) has landed in TMEM
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
-              uint32_t t0[32];
-              tmem_ld32(tO + c * 32, t0);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * alpha);
-              tmem_st32(tO + c * 32, t0);
-            }
-            tmem_st_wait();
-            l0 *= alpha;
-            l1 *= alpha;
-          }
-          if (need) m = mxl;
-        } else if (j > 0) {
-          mbar_wait(&o_full[x], (j - 1) & 1);            // P(j-1) has been consumed: its buffer may be overwritten
-        }
-        // ---- P = exp2(s * scale - m) -> bf16 -> shared memory (K-major SW128), row sum in two packed lanes
-        const float nm = -m;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < nchunk) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a0, a1, e0, e1;
-              fma2(a0, a1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sc, nm);
-              if ((i & 7) < kPolyOf8) {
-                exp2_poly2(e0, e1, a0, a1);
-              } else {
-                e0 = exp2_approx(a0);
-                e1 = exp2_approx(a1);
-              }
-              add2(l0, l1, l0, l1, e0, e1);
-              pk[i] = pack_bf16(e0, e1);
-            }
-            uint8_t* pblk = prow + (c >> 1) * (kTileQ * 128);       // key block (64 keys) of this chunk
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
-              const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
-              *reinterpret_cast<uint4*>(pblk + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-            }
-          }
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        mbar_arrive(&p_full[x]);
-      }
-      // ---- last tile's P V, normalise, store
-      mbar_wait(&o_full[x], (nkv - 1) & 1);
-      tc_fence_after();
-      const int q = q_base + x * kTileQ + r;
-      const float inv = 1.f / (l0 + l1);
-      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D;
-#pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t t0[32];
-        tmem_ld32(tO + c * 32, t0);
-        tmem_ld_wait();
-        if (q < p.Tq) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(t0[8 * i]) * inv, __uint_as_float(t0[8 * i + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(t0[8 * i + 2]) * inv, __uint_as_float(t0[8 * i + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(t0[8 * i + 4]) * inv, __uint_as_float(t0[8 * i + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(t0[8 * i + 6]) * inv, __uint_as_float(t0[8 * i + 7]) * inv);
-            reinterpret_cast<uint4*>(op + c * 32)[i] = o;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-}
-
-template <int D, int NQ>
-static int launch_attention2(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                             cudaStream_t stream) {
-  using Cfg = Attn2Cfg<D, NQ>;
-  static_assert(Cfg::kSmem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention2)");
-    configured = true;
-  }
-  dim3 grid((p.Tq + kTileQ * NQ - 1) / (kTileQ * NQ), p.heads, p.batch);
-  cudaError_t e = launch_kernel(attention2_kernel<D, NQ>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
-  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention2 launch");
-}
-
-// One softmax thread's whole KV loop (shared by attention512_kernel; same arithmetic as the softmax branch of
-// attention2_kernel): tS / tO = TMEM addresses of this thread's S row (128 columns) and O row (OW columns), prow = its
-// row of the P tile in shared memory (two K-major SW128 blocks 128 x 64), swz = row & 7.
+// One softmax thread's whole KV loop (attention2_kernel and attention512_kernel): tS / tO / tP = TMEM addresses of this
+// thread's S row (128 fp32 columns), O row (OW fp32 columns) and P row (64 columns holding 128 bf16: P is the A operand
+// of the P V tensor-core product and is read from tensor memory, so it never touches shared memory -- with P in shared
+// memory the kernel was bound by shared-memory bandwidth: 32 KB of P stores + 32 KB of UMMA reads per 128 x 128 tile on
+// top of the Q / K / V operand reads).
 template <int OW>
-__device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint8_t* prow, uint32_t swz, uint64_t* s_full,
+__device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint32_t tP, uint64_t* s_full,
                                              uint64_t* s_empty, uint64_t* p_full, uint64_t* o_full, int nkv, int Tk,
                                              float sc, bf16* op, bool row_valid) {
   float m = -INFINITY, mrun = -INFINITY, l0 = 0.f, l1 = 0.f;
@@ -801,16 +506,11 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint8_t* 
           add2(l0, l1, l0, l1, e0, e1);
           pk[i] = pack_bf16(e0, e1);
         }
-        uint8_t* pblk = prow + (c >> 1) * (kTileQ * 128);
-#pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
-          *reinterpret_cast<uint4*>(pblk + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
-        }
+        tmem_st16(tP + c * 16, pk);          // keys [32 c, 32 c + 32) of this row: 16 packed bf16 pairs
       }
     }
+    tmem_st_wait();
     tc_fence_before();
-    fence_proxy_async_smem();
     mbar_arrive(p_full);
   }
   mbar_wait(o_full, (nkv - 1) & 1);
@@ -835,6 +535,194 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint8_t* 
   }
 }
 
+template <int D, int NQ>
+struct Attn2Cfg {
+  static constexpr int kStages = D == 64 ? 4 : 3;
+  static constexpr int kQBytes = kTileQ * D * 2;
+  static constexpr int kKBytes = kTileK * D * 2;
+  static constexpr int kSmem = NQ * kQBytes + kStages * 2 * kKBytes + 1024;
+  static constexpr int kThreads = (4 + 4 * NQ) * 32;      // warp group 0: TMA, MMA, 2 idle warps; then 4 warps per query tile
+  // TMEM columns: S [0, 128 NQ), O [128 NQ, 128 NQ + D NQ), P (bf16 pairs) [128 NQ + D NQ, + 64 NQ)
+  static constexpr int kColO = NQ * 128, kColP = NQ * 128 + NQ * D;
+  static constexpr uint32_t kTmemCols = 512;
+  static_assert(kColP + NQ * 64 <= 512, "tensor memory budget");
+};
+
+template <int D, int NQ>
+__global__ void __launch_bounds__(Attn2Cfg<D, NQ>::kThreads, 1)
+attention2_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
+                  const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
+  using Cfg = Attn2Cfg<D, NQ>;
+  constexpr int ND = D / 64;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kQBytes = Cfg::kQBytes, kKBytes = Cfg::kKBytes;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                   // [NQ] x [ND blocks of 128 rows x 128 B]
+  uint8_t* sKV = sQ + NQ * kQBytes;                     // stage s: K at s * 2 * kKBytes, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * 2 * kKBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = q_full + 1;                       // [kStages]
+  uint64_t* kv_empty = kv_full + kStages;               // [kStages]
+  uint64_t* s_full = kv_empty + kStages;                // [NQ]
+  uint64_t* s_empty = s_full + NQ;                      // [NQ]
+  uint64_t* p_full = s_empty + NQ;                      // [NQ]
+  uint64_t* o_full = p_full + NQ;                       // [NQ]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
+
+  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const int q_base = blockIdx.x * (kTileQ * NQ);
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = (p.Tk + kTileK - 1) / kTileK;
+  const int nq_act = (NQ == 2 && q_base + kTileQ < p.Tq) ? 2 : 1;     // query tiles of this CTA that hold rows
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int x = 0; x < NQ; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&s_empty[x], 128);
+      mbar_init(&p_full[x], 128);
+      mbar_init(&o_full[x], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
+  // (each setmaxnreg sits inside its role's branch: after a control-flow merge ptxas would apply the smaller budget
+  //  to every role)
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one_sync()) {
+      mbar_expect_tx(q_full, nq_act * kQBytes);
+      for (int x = 0; x < nq_act; ++x)
+#pragma unroll
+        for (int nb = 0; nb < ND; ++nb)
+          tma_load_3d(sQ + x * kQBytes + nb * (kTileQ * 128), &mapQ, q_full, h * D + nb * 64, q_base + x * kTileQ, b);
+    }
+    __syncwarp();
+    const int bk = p.kv_shared ? 0 : b;
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % kStages;
+      mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
+      uint8_t* sk = sKV + s * 2 * kKBytes;
+      if (elect_one_sync()) {
+        mbar_expect_tx(&kv_full[s], 2 * kKBytes);
+#pragma unroll
+        for (int nb = 0; nb < ND; ++nb) {
+          tma_load_3d(sk + nb * (kTileK * 128), &mapK, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
+          tma_load_3d(sk + kKBytes + nb * (kTileK * 128), &mapV, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
+        }
+      }
+      __syncwarp();
+    }
+   } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
+    const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
+    mbar_wait(q_full, 0);
+    auto issue_s = [&](int x, int j) {          // S_x(j) = Q_x K_j^T -> TMEM columns [128 x, 128 x + 128)
+      const int s = j % kStages;
+      if (x == 0) mbar_wait(&kv_full[s], (j / kStages) & 1);       // (x = 1 follows x = 0 of the same j)
+      tc_fence_after();
+      const uint32_t aK = aKV + s * 2 * kKBytes;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int nb = 0; nb < ND; ++nb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_bf16(tmem_base + x * 128, umma_desc_k_sw128(aQ + x * kQBytes + nb * (kTileQ * 128)) + 2 * k,
+                        umma_desc_k_sw128(aK + nb * (kTileK * 128)) + 2 * k, idesc_s, (nb | k) != 0 ? 1u : 0u);
+        tc_commit(&s_full[x]);
+      }
+      __syncwarp();
+    };
+    for (int x = 0; x < nq_act; ++x) issue_s(x, 0);
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % kStages;
+      const uint32_t aV = aKV + s * 2 * kKBytes + kKBytes;
+      // k-steps of 16 keys that hold valid keys (the last KV tile may be partial; P columns past them are not written)
+      const int kvalid = min(kTileK, p.Tk - j * kTileK);
+      const int nk16 = ((kvalid + 31) >> 5) << 1;
+      for (int x = 0; x < nq_act; ++x) {
+        if (j + 1 < nkv) {
+          mbar_wait(&s_empty[x], j & 1);        // group x holds S_x(j) in registers
+          issue_s(x, j + 1);                    // runs under the softmax of tile j
+        }
+        mbar_wait(&p_full[x], j & 1);           // P_x(j) in tensor memory, O_x rescaled if it had to be
+        tc_fence_after();
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int nb = 0; nb < ND; ++nb) {
+            for (int k = 0; k < nk16; ++k) {     // A = P from TMEM: 16 keys = 8 columns of bf16 pairs per k-step
+              const uint64_t db = umma_desc_mn_sw128(aV + nb * (kTileK * 128) + k * 16 * 128, kTileK * 128);
+              tc_mma_bf16_ts(tmem_base + Cfg::kColO + x * D + nb * 64, tmem_base + Cfg::kColP + x * 64 + 8 * k, db,
+                             idesc_pv, (j | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&o_full[x]);
+          if (x == nq_act - 1) tc_commit(&kv_empty[s]);
+        }
+        __syncwarp();
+      }
+    }
+   }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // =============================== softmax / output: one thread per query row ===============================
+    const int x = (warp - 4) >> 2;                       // query tile (softmax group)
+    const int qd = warp & 3;                             // TMEM lane quarter this warp may access
+    const int r = qd * 32 + lane;
+    if (x < nq_act) {
+      const uint32_t tl = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+      const int q = q_base + x * kTileQ + r;
+      softmax_rows<D>(tl + x * 128, tl + Cfg::kColO + x * D, tl + Cfg::kColP + x * 64, &s_full[x], &s_empty[x], &p_full[x],
+                      &o_full[x], nkv, p.Tk, p.scale_log2,
+                      p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D, q < p.Tq);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int D, int NQ>
+static int launch_attention2(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                             cudaStream_t stream) {
+  using Cfg = Attn2Cfg<D, NQ>;
+  static_assert(Cfg::kSmem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention2)");
+    configured = true;
+  }
+  dim3 grid((p.Tq + kTileQ * NQ - 1) / (kTileQ * NQ), p.heads, p.batch);
+  cudaError_t e = launch_kernel(attention2_kernel<D, NQ>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention2 launch");
+}
+
 // =====================================================================================================================
 // attention512_kernel: flash attention for ONE 512-wide head (the VAE mid-block Attention of autoencoder.py:32,44:
 // diffusers Attention(512, heads=1, dim_head=512) over all 4 096 / 16 384 latent pixels).  Replaces the GEMM -> fp32
@@ -842,26 +730,24 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint8_t* 
 //
 //   O[128 x 512] fp32 would need all 512 TMEM columns, leaving none for S: the output columns are split in two halves
 //   and a CTA owns (128-query tile, column half, image); both halves compute S = Q K^T (1.5x the minimal FLOPs, the
-//   price of keeping S and O on chip).  TMEM: S 128 + O 256 columns.
-//   Q (128 x 512, 128 KB) stays resident in shared memory; K_j streams through a 4-stage ring as eight 64-channel
+//   price of keeping S and O on chip).  TMEM: S 128 + O 256 + P 64 columns (P is the TMEM A operand of P V).
+//   Q (128 x 512, 128 KB) stays resident in shared memory; K_j streams through a 6-stage ring as eight 64-channel
 //   chunks (S accumulates over them), V_j as four 64-column chunks of this CTA's half, all 16 KB boxes:
 //     warp 0 TMA producer   K(0); then per KV tile j:  K(j+1) chunks, V(j) chunks      (the MMA warp's consumption order)
 //     warp 1 tcgen05 issuer S(0); then per j: [s_empty(j)] S(j+1);  [p_full(j)] O += P(j) V(j)
 //     warps 4..7 softmax, one thread per query row -- same single-pass arithmetic as attention2_kernel.
 //   The main loop is tensor-bound (3 072 tensor cycles per KV tile against ~700 softmax cycles).
 // =====================================================================================================================
-constexpr int kD5 = 512, kOW5 = 256, kRing5 = 4, kChunk5 = kTileK * 64 * 2;     // 16 KB ring stages
+constexpr int kD5 = 512, kOW5 = 256, kRing5 = 6, kChunk5 = kTileK * 64 * 2;     // 16 KB ring stages
 
 __global__ void __launch_bounds__(256, 1)
 attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
                     const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
   constexpr int kQBytes = kTileQ * kD5 * 2;             // 128 KB: 8 blocks of [128 rows x 128 B]
-  constexpr int kPBytes = kTileQ * kTileK * 2;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sR = sQ + kQBytes;                           // ring: kRing5 x 16 KB
-  uint8_t* sP = sR + kRing5 * kChunk5;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + kRing5 * kChunk5);
   uint64_t* q_full = bars;
   uint64_t* r_full = q_full + 1;                        // [kRing5]
   uint64_t* r_empty = r_full + kRing5;                  // [kRing5]
@@ -935,8 +821,8 @@ attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant_
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V chunk) is MN-major
-    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aR = smem_u32(sR);
-    const uint32_t tS = tmem_base, tO = tmem_base + 128;
+    const uint32_t aQ = smem_u32(sQ), aR = smem_u32(sR);
+    const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 128 + kOW5;
     int it = 0;
     mbar_wait(q_full, 0);
     auto issue_s = [&]() {                    // S = sum over eight 64-channel chunks of Q_c K_c^T
@@ -969,9 +855,8 @@ attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant_
         tc_fence_after();
         if (elect_one_sync()) {
           for (int k = 0; k < nk16; ++k) {
-            const uint64_t da = umma_desc_k_sw128(aP + (k >> 2) * (kTileQ * 128)) + 2 * (k & 3);
             const uint64_t db = umma_desc_mn_sw128(aR + s * kChunk5 + k * 16 * 128, kTileK * 128);
-            tc_mma_bf16(tO + c * 64, da, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            tc_mma_bf16_ts(tO + c * 64, tP + 8 * k, db, idesc_pv, (j | k) != 0 ? 1u : 0u);
           }
           tc_commit(&r_empty[s]);
         }
@@ -988,7 +873,7 @@ attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant_
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const int q = q0 + r;
-    softmax_rows<kOW5>(tmem_base + lane_off, tmem_base + lane_off + 128, sP + r * 128, static_cast<uint32_t>(r & 7),
+    softmax_rows<kOW5>(tmem_base + lane_off, tmem_base + lane_off + 128, tmem_base + lane_off + 128 + kOW5,
                        s_full, s_empty, p_full, o_full, nkv, p.Tk, p.scale_log2,
                        p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * kD5 + half * kOW5, q < p.Tq);
   }
@@ -1003,7 +888,7 @@ attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant_
 
 static int launch_attention512(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                                cudaStream_t stream) {
-  constexpr int smem = kTileQ * kD5 * 2 + kRing5 * kChunk5 + kTileQ * kTileK * 2 + 1024;
+  constexpr int smem = kTileQ * kD5 * 2 + kRing5 * kChunk5 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {

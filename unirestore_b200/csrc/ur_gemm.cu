@@ -378,18 +378,21 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   if ((reinterpret_cast<uintptr_t>(d->x1) | reinterpret_cast<uintptr_t>(d->x2) | reinterpret_cast<uintptr_t>(d->w)) & 15)
     return set_error(UR_ERR_ARG, "ur_conv_gemm: pointers must be 16-byte aligned");
 
-  // ---- M tile shape: minimise padded work, prefer wide tiles
-  int best_w = 0, best_h = 0;
+  // ---- M tile shape: minimise padded work; among equal tile counts take the fewest images per tile (an image's rows
+  //      stay together: the epilogue statistics need >= 32 rows of a tile per image, and the TMA boxes are denser),
+  //      then the widest tile
+  int best_w = 0, best_h = 0, best_bt = 0;
   long long best_cost = -1;
   for (int wl = 7; wl >= 0; --wl) {
     for (int hl = 0; wl + hl <= 7; ++hl) {
       const int Wt = 1 << wl, Ht = 1 << hl, Bt = 128 >> (wl + hl);
       if (d->w_batched && Bt != 1) continue;
       const long long tiles = 1LL * ((d->wout + Wt - 1) / Wt) * ((d->hout + Ht - 1) / Ht) * ((d->batch + Bt - 1) / Bt);
-      if (best_cost < 0 || tiles < best_cost) {
+      if (best_cost < 0 || tiles < best_cost || (tiles == best_cost && Bt < best_bt)) {
         best_cost = tiles;
         best_w = wl;
         best_h = hl;
+        best_bt = Bt;
       }
     }
   }
