@@ -71,26 +71,34 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
                                   bf16* __restrict__ out, long long ldo, long long iso) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float sh[];  // mean[G], rstd[G]
+  extern __shared__ __align__(16) double shd[];  // per-channel (sum, sumsq) [C][2] as doubles, then mean[G], rstd[G] floats
+  float* sh = reinterpret_cast<float*>(shd + 2 * (C1 + C2));
   const int C = C1 + C2;
   const int cg = C / G;
   const int b = blockIdx.y;
-  // statistics of channel c: one array over cat(x1, x2), or one array per source
+  // statistics of channel c: one array over cat(x1, x2), or one array per source.  Every thread fetches whole
+  // (sum, sumsq) pairs in ONE round trip to L2 (16-byte loads) -- a serial walk over the cg channels of a group by G
+  // threads cost cg dependent L2 latencies at the head of every block -- then G threads reduce from shared memory.
   const double* st1 = stats + static_cast<long long>(b) * (stats2 ? C1 : C) * 2;
   const double* st2 = stats2 ? stats2 + static_cast<long long>(b) * C2 * 2 - 2 * C1 : st1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double2 v = *reinterpret_cast<const double2*>((c < C1 ? st1 : st2) + 2 * c);
+    shd[2 * c] = v.x;
+    shd[2 * c + 1] = v.y;
+  }
+  __syncthreads();
   const double inv_n = 1.0 / (static_cast<double>(P) * cg);
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double s = 0.0, q = 0.0;
     for (int c = g * cg; c < (g + 1) * cg; ++c) {
-      const double* st = c < C1 ? st1 : st2;
-      s += st[2 * c];
-      q += st[2 * c + 1];
+      s += shd[2 * c];
+      q += shd[2 * c + 1];
     }
     const double mean = s * inv_n;
     double var = q * inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     sh[g] = static_cast<float>(mean);
-    sh[G + g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    sh[G + g] = rsqrtf(static_cast<float>(var) + eps);
   }
   __syncthreads();
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
@@ -301,7 +309,13 @@ extern "C" int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, c
   int CV, PL, chunk, nchunks;
   pick_block(C, pixels, CV, PL, chunk, nchunks, batch);
   dim3 grid(nchunks, batch);
-  launch_kernel(norm_apply_kernel, dim3(grid), dim3(CV * PL), 2 * groups * sizeof(float), stream, 
+  static bool configured = false;
+  if (!configured) {          // up to C = 8192 channels of fp64 statistics staged in shared memory
+    cudaError_t e = cudaFuncSetAttribute(norm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(norm_apply)");
+    configured = true;
+  }
+  launch_kernel(norm_apply_kernel, dim3(grid), dim3(CV * PL), 2 * groups * sizeof(float) + 2 * static_cast<size_t>(C) * sizeof(double), stream, 
       static_cast<const bf16*>(x1), ld1, is1, c1, static_cast<const bf16*>(x2), ld2, is2, c2, stats, stats2, groups, pixels, CV,
       PL, chunk, gamma, beta, eps, silu, static_cast<bf16*>(out), ldo, iso);
   cudaError_t e = cudaGetLastError();
