@@ -168,3 +168,33 @@ def test_concat_channels_kernel():
     y = ops.conv_gemm(a[..., :72], w, 64, x2=b)
     ref = torch.nn.functional.linear(torch.cat([a[..., :72], b], -1).float(), w.float()).to(torch.bfloat16).float()
     assert_close(y, ref, 1e-3, "two-source conv with unaligned source 1")
+
+
+def test_forward_1024_vs_oracles():
+    """BASELINE configs[3] resolution: 1024x1024 -> latent 128x128, i.e. 16 384-token UNet self-attention
+    (base_model.py:138) and the VAE mid-block head over 16 384 tokens (autoencoder.py:32) through attention512_kernel
+    (no 1 GB score tensor).  B=1, 2 DDIM steps, graph path, against the rounded and the fp32 oracle on the GPU."""
+    from oracle import rounded as R
+    from oracle import unirestore as O
+    from unirestore_b200.diffuie import DiffUIE
+    from unirestore_b200.init_utils import deterministic_init_
+    cfg = (CFG20[0], dict(CFG20[1], num_inference_steps=2), CFG20[2])
+    o = deterministic_init_(O.DiffUIE(*cfg)).eval().requires_grad_(False)
+    m = DiffUIE(*cfg).eval().requires_grad_(False)
+    m.load_state_dict(o.state_dict(), strict=True)
+    o, m = o.to(DEV), m.to(DEV)
+    g = torch.Generator().manual_seed(31)
+    img = torch.rand(1, 3, 1024, 1024, generator=g).to(DEV)
+    noise = (torch.randn(1, 4, 128, 128, generator=g).to(DEV), torch.randn(1, 4, 128, 128, generator=g).to(DEV))
+    m.use_cuda_graph = True
+    y = m(img, "ir", noise=noise)
+    y = m(img, "ir", noise=noise)
+    with torch.no_grad():
+        y_q = R.forward(o, img, "ir", noise=noise)
+        torch.cuda.empty_cache()
+        with R.exact():
+            y_f = R.forward(o, img, "ir", noise=noise)
+    assert_close(y, y_q, 1.2e-2, "1024x1024 B=1 2 steps, graph path vs rounded oracle (image)")
+    assert_close(y, y_f, 1.5e-2, "1024x1024 B=1 2 steps, graph path vs fp32 oracle (image)")
+    del o, m
+    torch.cuda.empty_cache()

@@ -1,0 +1,151 @@
+"""Per-kernel-family roofline report of one DiffUIE.forward (BASELINE configs[4] "roofline report per kernel").
+
+Every ops.* entry point is wrapped with CUDA events (eager, one stream, PDL off so kernels do not overlap) and its
+ALGORITHMIC work is computed from the call's shapes with the counting rules of SURVEY.md 8d / Appendix C:
+    conv / linear        FLOPs = 2 * B*Ho*Wo * N * taps * K_per_tap     bytes = 2*(input) + out + 2*weights (+ residual)
+    attention            FLOPs = 4 * B * Tq * Tk * C                     bytes = 2*(q + k + v + out)
+    norm / elementwise   bytes = read + written tensors
+Fractions: tensor = TFLOP/s / bf16_tflops_sustained, hbm = GB/s / hbm_gbs (MEASURED_PEAKS.json); the binding roof of a
+family is the larger of the two.  Markdown on stdout:
+    python tools/roofline_report.py [--batch 8 --size 512 --steps 20] > profiles/roofline_r2.md
+"""
+import argparse
+import collections
+import json
+import os
+import sys
+
+os.environ["UR_PDL"] = "0"          # development switch of the library: no programmatic dependent launch (no kernel overlap)
+import torch  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import CFG, cheap_init_  # noqa: E402
+from unirestore_b200 import ops  # noqa: E402
+from unirestore_b200.diffuie import DiffUIE  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--size", type=int, default=512)
+ap.add_argument("--steps", type=int, default=20)
+ap.add_argument("--task", default="ir")
+a = ap.parse_args()
+dev = "cuda:0"
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+PT, PH = float(peaks["bf16_tflops_sustained"]), float(peaks["hbm_gbs"])
+
+cfg = (CFG[0], dict(CFG[1], num_inference_steps=a.steps), CFG[2])
+m = cheap_init_(DiffUIE(*cfg)).eval().requires_grad_(False).to(dev)
+m.overlap_controller = False
+m.base_model.overlap_sc_tuner = False
+img = torch.rand(a.batch, 3, a.size, a.size, device=dev)
+for _ in range(2):
+    m(img, a.task)
+torch.cuda.synchronize()
+
+rec = collections.defaultdict(lambda: [0, 0.0, 0.0, []])      # family -> [launches, flops, bytes, events]
+
+
+def nbytes(t):
+    return 0 if t is None else t.numel() * t.element_size()
+
+
+def conv_family(x, w, n, kw):
+    taps = len(kw.get("taps", ops.TAPS_1x1))
+    x4 = ops._as4(x)
+    B, H, W, C1 = x4.shape
+    c2 = kw["x2"].shape[-1] if kw.get("x2") is not None else 0
+    stride = kw.get("stride", 1)
+    ho, wo = kw.get("hout") or H // stride, kw.get("wout") or W // stride
+    gk = kw.get("group_kc", 0)
+    kper = gk if gk else C1 + c2
+    flops = 2.0 * B * ho * wo * n * taps * kper
+    act = kw.get("act", 0)
+    n_out = n // 2 if act in (ops.UR_ACT_GEGLU, ops.UR_ACT_GATE) else n
+    osz = 4 if kw.get("out_dtype", torch.bfloat16) == torch.float32 else 2
+    byts = 2.0 * B * H * W * (C1 + c2) + osz * B * ho * wo * n_out + nbytes(w) + (2.0 * B * ho * wo * n_out if kw.get("residual") is not None else 0)
+    if act == ops.UR_ACT_GEGLU:
+        fam = "linear + GEGLU epilogue (K=%d)" % kper
+    elif act == ops.UR_ACT_GATE:
+        fam = "1x1 conv + SimpleGate epilogue"
+    elif gk:
+        fam = "grouped conv3x3 (+GELU)"
+    elif taps >= 9 and stride == 2:
+        fam = "conv3x3 stride 2"
+    elif taps == 4:
+        fam = "upsample conv (sub-pixel 2x2 phases)"
+    elif taps >= 9:
+        fam = "conv3x3 C>=128" if C1 + c2 >= 128 else "conv3x3 stem/head (C<128)"
+    elif kper <= 640:
+        fam = "1x1 conv / linear, K<=640"
+    else:
+        fam = "1x1 conv / linear, K>640"
+    return fam, flops, byts
+
+
+def wrap(name, cost):
+    fn = getattr(ops, name)
+
+    def w(*args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn(*args, **kw)
+        e.record()
+        fam, fl, by = cost(r, *args, **kw)
+        R = rec[fam]
+        R[0] += 1
+        R[1] += fl
+        R[2] += by
+        R[3].append((s, e))
+        return r
+    setattr(ops, name, w)
+
+
+def out_bytes(r):
+    if isinstance(r, (tuple, list)):
+        return sum(nbytes(t) for t in r if isinstance(t, torch.Tensor))
+    return nbytes(r)
+
+
+wrap("conv_gemm", lambda r, x, w, n, **kw: conv_family(x, w, n, kw))
+wrap("attention", lambda r, q, k, v, heads, **kw: (
+    "attention head_dim %d" % (q.shape[-1] // heads), 4.0 * q.shape[0] * q.shape[1] * k.shape[1] * q.shape[2],
+    2.0 * (q.shape[0] * q.shape[1] * q.shape[2] * 2 + 2 * k.shape[0] * k.shape[1] * q.shape[2])))
+wrap("norm_apply", lambda r, x, st, *a_, **kw: ("GroupNorm / InstanceNorm apply (+SiLU)", 0.0, 2.0 * nbytes(r)))
+wrap("chan_stats", lambda r, x, **kw: ("channel statistics pass", 0.0, float(nbytes(x))))
+wrap("layernorm", lambda r, x, *a_, **kw: ("LayerNorm / LayerNorm2d", 0.0, 2.0 * nbytes(x)))
+wrap("dwconv3x3_gate", lambda r, x, *a_, **kw: ("depthwise 3x3 + SimpleGate + GAP", 0.0, 1.5 * nbytes(x)))
+wrap("scale_channels_", lambda r, x, *a_, **kw: ("channel scale (in place)", 0.0, 2.0 * nbytes(x)))
+for nm in ("small_linear", "timestep_embedding", "adanaf_scales", "tfa_gates", "posterior_sample", "latent_axpby", "ddim_step_",
+           "image_to_nhwc8", "nhwc_to_image", "resize_pad"):
+    wrap(nm, (lambda nm: lambda r, *args, **kw: ("small / latent / image kernels", 0.0,
+                                                 float(out_bytes(r) + sum(nbytes(t) for t in args if isinstance(t, torch.Tensor)))))(nm))
+
+torch.cuda.synchronize()
+s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s0.record()
+m(img, a.task)
+e0.record()
+torch.cuda.synchronize()
+rows, tot_t, tot_f, tot_b = [], 0.0, 0.0, 0.0
+for fam, (n, fl, by, evs) in rec.items():
+    t = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+    rows.append((t, fam, n, fl, by))
+    tot_t += t
+    tot_f += fl
+    tot_b += by
+rows.sort(reverse=True)
+print("# Per-kernel-family roofline, DiffUIE.forward B=%d %dx%d %d DDIM steps task '%s' (round 2)\n" % (a.batch, a.size, a.size, a.steps, a.task))
+print("Eager, one stream, PDL off (`tools/roofline_report.py`); CUDA events around every C-ABI call; algorithmic FLOPs / bytes by the "
+      "SURVEY.md 8d counting rules.  Peaks (MEASURED_PEAKS.json): %.0f TFLOP/s sustained bf16, %.0f GB/s HBM.  "
+      "`frac` = larger of the two fractions = the family's binding roof.\n" % (PT, PH))
+print("Summed kernel time %.1f ms per forward (graph-replayed forward with side streams: see the bench line); "
+      "%.1f TFLOP algorithmic -> %.0f TFLOP/s overall = %.1f %% of the sustained tensor roof.\n"
+      % (tot_t * 1e3, tot_f / 1e12, tot_f / tot_t / 1e12, 100 * tot_f / tot_t / 1e12 / PT))
+print("| family | launches | time ms | share | GFLOP | MB | TFLOP/s | GB/s | tensor frac | HBM frac | bound | frac |")
+print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---:|")
+for t, fam, n, fl, by in rows:
+    tf, gb = fl / t / 1e12, by / t / 1e9
+    ft, fh = tf / PT, gb / PH
+    print("| %s | %d | %.2f | %.1f %% | %.0f | %.0f | %.0f | %.0f | %.2f | %.2f | %s | %.2f |"
+          % (fam, n, t * 1e3, 100 * t / tot_t, fl / 1e9, by / 1e6, tf, gb, ft, fh, "tensor" if ft >= fh else "hbm", max(ft, fh)))
