@@ -915,7 +915,7 @@ static int launch_attention512(const AttnParams& p, const CUtensorMap& mq, const
 //       no atomics; the running maximum lives in registers and is identical in both threads;
 //     - P goes to tensor memory (tcgen05.st) and P V reads its A operand from TMEM;
 //     - packed f32x2 scale / sum, 3-input max, kPolyOf8 of every 8 exponential pairs on the FMA pipe.
-//   Registers: warp group 0 (TMA, MMA, two idle warps) shrinks to 40, the softmax warp groups grow to 112.
+//   Registers: warp group 0 (TMA, MMA, two idle warps) shrinks to 40, the softmax warp groups grow to 104.
 // =====================================================================================================================
 template <int D, int NQ>
 struct Attn3Cfg {
@@ -1062,8 +1062,11 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
     }
    }
   } else {
+    // setmaxnreg.inc only draws on registers released by setmaxnreg.dec INSIDE this CTA (the per-CTA pool): the kernel
+    // launches with 96 registers per thread (640 threads; 160 with 384), warp group 0 releases 128 x (96 - 40) = 7 168,
+    // so the 512 softmax threads can grow by at most 14 -> 104.  (Asking for 112 blocks forever: r2 call 6.)
     if constexpr (NQ == 2) {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     } else {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     }
