@@ -11,10 +11,12 @@ from unirestore_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--cases", default="self64,self32,cross64,ctrl64")
+ap.add_argument("--poly", type=int, default=3, help="exp2 pairs of every 8 on the FMA pipe (attention2 / 3)")
 ap.add_argument("--impl", type=int, default=2, help="attention kernel generation (1, 2 or 3)")
 a = ap.parse_args()
 from unirestore_b200 import _cabi  # noqa: E402
 _cabi.lib().ur_debug_set_attention_impl(a.impl)
+_cabi.lib().ur_debug_set_attention_poly(a.poly)
 CASES = {"self64": (8, 5, 64, 4096, 4096), "self32": (8, 10, 64, 1024, 1024), "cross64": (8, 5, 64, 4096, 77),
          "ctrl64": (8, 4, 64, 4096, 4096), "self16": (8, 20, 64, 256, 256), "self128": (4, 5, 64, 16384, 16384),
          "ctrl128": (8, 4, 128, 256, 256)}
@@ -38,4 +40,4 @@ for name in a.cases.split(","):
     torch.cuda.synchronize()
     t = s.elapsed_time(e) * 1e-3 / a.iters
     fl = 4.0 * B * Tq * Tk * C
-    print("impl%d %-8s B=%d h=%d d=%d Tq=%d Tk=%d  %8.1f us  %7.1f TF/s" % (a.impl, name, B, h, d, Tq, Tk, t * 1e6, fl / t / 1e12), flush=True)
+    print("impl%d poly%d %-8s B=%d h=%d d=%d Tq=%d Tk=%d  %8.1f us  %7.1f TF/s" % (a.impl, a.poly, name, B, h, d, Tq, Tk, t * 1e6, fl / t / 1e12), flush=True)

@@ -374,7 +374,7 @@ attention_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ C
 //   (setmaxnreg.dec 56) and the softmax warp groups grow to 224 (setmaxnreg.inc).
 // D = 128 (Controller low-resolution levels) runs with NQ = 1 and a 2-stage ring (shared-memory budget).
 // =====================================================================================================================
-constexpr int kPolyOf8 = 3;      // element pairs (of every 8) whose exp2 runs on the FMA pipe
+constexpr int kPolyOf8Default = 3;      // element pairs (of every 8) whose exp2 runs on the FMA pipe (template parameter POLY)
 
 __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
   asm("{\n.reg .b64 ra, rb, rc, rd;\n"
@@ -428,7 +428,7 @@ __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float
 // of the P V tensor-core product and is read from tensor memory, so it never touches shared memory -- with P in shared
 // memory the kernel was bound by shared-memory bandwidth: 32 KB of P stores + 32 KB of UMMA reads per 128 x 128 tile on
 // top of the Q / K / V operand reads).
-template <int OW>
+template <int OW, int POLY>
 __device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint32_t tP, uint64_t* s_full,
                                              uint64_t* s_empty, uint64_t* p_full, uint64_t* o_full, int nkv, int Tk,
                                              float sc, bf16* op, bool row_valid) {
@@ -497,7 +497,7 @@ __device__ __forceinline__ void softmax_rows(uint32_t tS, uint32_t tO, uint32_t 
         for (int i = 0; i < 16; ++i) {
           float a0, a1, e0, e1;
           fma2(a0, a1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sc, nm);
-          if ((i & 7) < kPolyOf8) {
+          if ((i & 7) < POLY) {
             exp2_poly2(e0, e1, a0, a1);
           } else {
             e0 = exp2_approx(a0);
@@ -548,7 +548,7 @@ struct Attn2Cfg {
   static_assert(kColP + NQ * 64 <= 512, "tensor memory budget");
 };
 
-template <int D, int NQ>
+template <int D, int NQ, int POLY>
 __global__ void __launch_bounds__(Attn2Cfg<D, NQ>::kThreads, 1)
 attention2_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
                   const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
@@ -693,7 +693,7 @@ attention2_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
     if (x < nq_act) {
       const uint32_t tl = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
       const int q = q_base + x * kTileQ + r;
-      softmax_rows<D>(tl + x * 128, tl + Cfg::kColO + x * D, tl + Cfg::kColP + x * 64, &s_full[x], &s_empty[x], &p_full[x],
+      softmax_rows<D, POLY>(tl + x * 128, tl + Cfg::kColO + x * D, tl + Cfg::kColP + x * 64, &s_full[x], &s_empty[x], &p_full[x],
                       &o_full[x], nkv, p.Tk, p.scale_log2,
                       p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D, q < p.Tq);
     }
@@ -707,19 +707,19 @@ attention2_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
   }
 }
 
-template <int D, int NQ>
+template <int D, int NQ, int POLY>
 static int launch_attention2(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                              cudaStream_t stream) {
   using Cfg = Attn2Cfg<D, NQ>;
   static_assert(Cfg::kSmem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention2)");
     configured = true;
   }
   dim3 grid((p.Tq + kTileQ * NQ - 1) / (kTileQ * NQ), p.heads, p.batch);
-  cudaError_t e = launch_kernel(attention2_kernel<D, NQ>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
+  cudaError_t e = launch_kernel(attention2_kernel<D, NQ, POLY>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention2 launch");
 }
 
@@ -873,7 +873,7 @@ attention512_kernel(const __grid_constant__ AttnParams p, const __grid_constant_
     const int r = qd * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
     const int q = q0 + r;
-    softmax_rows<kOW5>(tmem_base + lane_off, tmem_base + lane_off + 128, tmem_base + lane_off + 128 + kOW5,
+    softmax_rows<kOW5, kPolyOf8Default>(tmem_base + lane_off, tmem_base + lane_off + 128, tmem_base + lane_off + 128 + kOW5,
                        s_full, s_empty, p_full, o_full, nkv, p.Tk, p.scale_log2,
                        p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * kD5 + half * kOW5, q < p.Tq);
   }
@@ -928,7 +928,7 @@ struct Attn3Cfg {
   static_assert(kColP + NQ * 64 <= 512, "tensor memory budget");
 };
 
-template <int D, int NQ>
+template <int D, int NQ, int POLY>
 __global__ void __launch_bounds__(Attn3Cfg<D, NQ>::kThreads, 1)
 attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
                   const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
@@ -1153,7 +1153,7 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
             for (int i = 0; i < 16; ++i) {
               float a0, a1, e0, e1;
               fma2(a0, a1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sc, nm);
-              if ((i & 7) < kPolyOf8) {
+              if ((i & 7) < POLY) {
                 exp2_poly2(e0, e1, a0, a1);
               } else {
                 e0 = exp2_approx(a0);
@@ -1206,19 +1206,19 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
   }
 }
 
-template <int D, int NQ>
+template <int D, int NQ, int POLY>
 static int launch_attention3(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                              cudaStream_t stream) {
   using Cfg = Attn3Cfg<D, NQ>;
   static_assert(Cfg::kSmem <= 227 * 1024, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention3_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention3_kernel<D, NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention3)");
     configured = true;
   }
   dim3 grid((p.Tq + kTileQ * NQ - 1) / (kTileQ * NQ), p.heads, p.batch);
-  cudaError_t e = launch_kernel(attention3_kernel<D, NQ>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
+  cudaError_t e = launch_kernel(attention3_kernel<D, NQ, POLY>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention3 launch");
 }
 
@@ -1250,6 +1250,13 @@ using namespace ur;
 
 static long long* g_attn_trace = nullptr;
 static int g_attn_impl = 1;      // 1: attention_kernel (default: measured faster, r2c2); 2: attention2_kernel
+static int g_attn_poly = kPolyOf8Default;
+// development: exponential pairs (of every 8) evaluated by the FMA-pipe polynomial in attention2 / attention3 (0..3)
+extern "C" int ur_debug_set_attention_poly(int n) {
+  const int old = g_attn_poly;
+  if (n >= 0 && n <= 3) g_attn_poly = n;
+  return old;
+}
 // development: select the attention kernel generation (returns the previous one)
 extern "C" int ur_debug_set_attention_impl(int impl) {
   const int old = g_attn_impl;
@@ -1295,10 +1302,24 @@ extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void
   p.out_bs = out_bs;
   p.trace = g_attn_trace;
   if (head_dim == 512) return launch_attention512(p, mq, mk, mv, stream);
-  if (g_attn_impl == 3)
-    return head_dim == 64 ? launch_attention3<64, 2>(p, mq, mk, mv, stream) : launch_attention3<128, 1>(p, mq, mk, mv, stream);
-  if (g_attn_impl == 2)
-    return head_dim == 64 ? launch_attention2<64, 2>(p, mq, mk, mv, stream) : launch_attention2<128, 1>(p, mq, mk, mv, stream);
+  if (g_attn_impl == 3) {
+    if (head_dim == 128) return launch_attention3<128, 1, kPolyOf8Default>(p, mq, mk, mv, stream);
+    switch (g_attn_poly) {
+      case 0: return launch_attention3<64, 2, 0>(p, mq, mk, mv, stream);
+      case 1: return launch_attention3<64, 2, 1>(p, mq, mk, mv, stream);
+      case 2: return launch_attention3<64, 2, 2>(p, mq, mk, mv, stream);
+      default: return launch_attention3<64, 2, 3>(p, mq, mk, mv, stream);
+    }
+  }
+  if (g_attn_impl == 2) {
+    if (head_dim == 128) return launch_attention2<128, 1, kPolyOf8Default>(p, mq, mk, mv, stream);
+    switch (g_attn_poly) {
+      case 0: return launch_attention2<64, 2, 0>(p, mq, mk, mv, stream);
+      case 1: return launch_attention2<64, 2, 1>(p, mq, mk, mv, stream);
+      case 2: return launch_attention2<64, 2, 2>(p, mq, mk, mv, stream);
+      default: return launch_attention2<64, 2, 3>(p, mq, mk, mv, stream);
+    }
+  }
   dim3 grid((tq + kTileQ - 1) / kTileQ, heads, batch);
   return head_dim == 64 ? launch_attention<64>(p, mq, mk, mv, grid, stream)
                         : launch_attention<128>(p, mq, mk, mv, grid, stream);
