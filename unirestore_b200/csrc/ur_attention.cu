@@ -1041,9 +1041,15 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
       const int kvalid = min(kTileK, p.Tk - j * kTileK);
       const int nk16 = ((kvalid + 31) >> 5) << 1;
       for (int x = 0; x < nq_act; ++x) {
+        const bool trm = p.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 4 && j < 8;
+        long long* tq = p.trace + 64 + (x * 4 + (j - 4)) * 8;
+        if (trm) tq[0] = clock64();
         mbar_wait(&s_empty[x], j & 1);          // every softmax thread of tile x holds its part of S_x(j) in registers
+        if (trm) tq[1] = clock64();
         if (j + 1 < nkv) issue_s(x, j + 1);     // runs under the softmax of tile j
+        if (trm) tq[2] = clock64();
         mbar_wait(&p_full[x], j & 1);           // P_x(j) in tensor memory, O_x rescaled if it had to be
+        if (trm) tq[3] = clock64();
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -1058,6 +1064,7 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
           if (x == nq_act - 1) tc_commit(&kv_empty[s]);
         }
         __syncwarp();
+        if (trm) tq[4] = clock64();
       }
     }
    }
@@ -1088,13 +1095,18 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
       for (int j = 0; j < nkv; ++j) {
         const int kvalid = p.Tk - j * kTileK - hf * 64;       // keys of this thread's half that exist (may be <= 0)
         const int nchunk = kvalid >= 64 ? 2 : (kvalid <= 0 ? 0 : ((kvalid + 31) >> 5));
+        const bool trs = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0 && hf == 0 && j >= 4 && j < 8;
+        long long* tp = p.trace + (x * 4 + (j - 4)) * 8;
+        if (trs) tp[0] = clock64();
         mbar_wait(&s_full[x], j & 1);
+        if (trs) tp[1] = clock64();
         tc_fence_after();
         uint32_t v[2][32];
 #pragma unroll
         for (int c = 0; c < 2; ++c)
           if (c < nchunk) tmem_ld32(tS + c * 32, v[c]);
         tmem_ld_wait();
+        if (trs) tp[2] = clock64();
         tc_fence_before();
         mbar_arrive(&s_empty[x]);
         if (kvalid < 64) {
@@ -1120,6 +1132,7 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
         slot[hf * 128 + r] = fmaxf(mx0, mx1);
         asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
         mrun = max3(mrun, slot[r], slot[128 + r]);
+        if (trs) tp[3] = clock64();
         const float mxl = mrun * sc;
         const bool need = (j == 0) || (mxl - m > 8.0f);        // identical in both threads of the row
         if (__any_sync(0xffffffffu, need)) {
@@ -1144,6 +1157,7 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
         } else if (j > 0) {
           mbar_wait(&o_full[x], (j - 1) & 1);    // P(j-1) V(j-1) has consumed the P columns this tile overwrites
         }
+        if (trs) tp[4] = clock64();
         const float nm = -m;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -1165,9 +1179,11 @@ attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ 
             tmem_st16(tP + c * 16, pk);
           }
         }
+        if (trs) tp[5] = clock64();
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
+        if (trs) tp[6] = clock64();
       }
       // ---- last tile's P V, combine the two partial row sums, normalise, store
       mbar_wait(&o_full[x], (nkv - 1) & 1);

@@ -255,6 +255,52 @@ __device__ __forceinline__ float erf_as_f(float x) {
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752f)); }
 
+// ---- packed f32x2 arithmetic (FFMA2 / FMUL2 / FADD2: one instruction per PAIR of fp32 lanes) -- epilogues and softmax
+// loops are issue-bound, so halving the FMA-pipe instruction count is worth more than it looks
+struct f2 {
+  float x, y;
+};
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\n"
+      "mov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0, %1}, rd;\n}\n"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ f2 splat2(float v) { return f2{v, v}; }
+// exact-erf GELU of a pair: the arithmetic of gelu_erf_f (Abramowitz-Stegun 7.1.26) with the polynomial, the argument
+// products and the final combination on packed instructions; 4 MUFU (2 rcp, 2 ex2) + ~9 packed + 4 scalar ops per pair
+__device__ __forceinline__ f2 gelu_erf2(f2 x) {
+  const f2 xs = mul2(x, splat2(0.70710678118654752f));
+  const f2 ax = f2{fabsf(xs.x), fabsf(xs.y)};
+  const f2 den = fma2(ax, splat2(0.3275911f), splat2(1.0f));
+  const f2 t = f2{__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)};
+  f2 pl = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
+  pl = fma2(pl, t, splat2(1.421413741f));
+  pl = fma2(pl, t, splat2(-0.284496736f));
+  pl = fma2(pl, t, splat2(0.254829592f));
+  const f2 nx2 = mul2(ax, f2{-ax.x * 1.4426950408889634f, -ax.y * 1.4426950408889634f});      // -x^2 log2(e)
+  const f2 e = f2{exp2_approx(nx2.x), exp2_approx(nx2.y)};
+  const f2 pt = mul2(pl, t);
+  const f2 y = fma2(f2{-pt.x, -pt.y}, e, splat2(1.0f));                                         // erf(|x|)
+  const f2 erfv = f2{copysignf(y.x, xs.x), copysignf(y.y, xs.y)};
+  const f2 hx = mul2(x, splat2(0.5f));
+  return fma2(hx, erfv, hx);                                                                      // 0.5 x (1 + erf)
+}
+
 // 16-byte vector reduction into global memory (sm_90+): four fp32 adds in one L2 atomic transaction
 __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

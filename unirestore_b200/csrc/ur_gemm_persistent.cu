@@ -434,39 +434,60 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
             rres[i] = (okc && roff[i] >= 0) ? __ldg(reinterpret_cast<const uint4*>(p.residual + roff[i] + col))
                                              : make_uint4(0u, 0u, 0u, 0u);
         }
-        float f[32];
-        if (plain) {
-          tmem_ld_wait();
-          if (tre) p.trace[320 + (c >> 6) * 8 + 2] = clock64();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 ad = *reinterpret_cast<const float4*>(add + c + 4 * j);
-            f[4 * j] = __uint_as_float(va[4 * j]) + ad.x;
-            f[4 * j + 1] = __uint_as_float(va[4 * j + 1]) + ad.y;
-            f[4 * j + 2] = __uint_as_float(va[4 * j + 2]) + ad.z;
-            f[4 * j + 3] = __uint_as_float(va[4 * j + 3]) + ad.w;
-          }
-        } else {
-          uint32_t vg[32];
-          if (gated) tmem_ld32(trow + (BN >> 1) + c, vg);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(va[j]) * p.alpha + add[c + j];
-            if (gated) {
-              const float g = __uint_as_float(vg[j]) * p.alpha + add[(BN >> 1) + c + j];
-              v = (p.act == UR_ACT_GEGLU) ? v * gelu_erf_f(g) : v * g;
-            } else if (p.act == UR_ACT_SILU) {
-              v = silu_f(v);
-            } else if (p.act == UR_ACT_GELU) {
-              v = gelu_erf_f(v);
-            }
-            f[j] = has_mul ? v * mul[c + j] : v;
-          }
-        }
-        // own row: (+ residual) -> bf16 -> staging (swizzled)
+        // accumulators -> (+bias / temb) -> activation / gate -> (* channel scale) -> (+residual) -> bf16 -> staging,
+        // EIGHT columns (one 16-byte staging chunk) at a time: the gated / GELU epilogues are issue- and latency-bound,
+        // and with all 32 columns of a, g and the results live (96 registers) the scheduler had no registers left to
+        // overlap the activation chains (GEGLU with K = 320 ran at 0.19 of the tensor roof, r2 roofline); a chunk keeps
+        // ~24 values live and its 4 pairs run on packed f32x2 instructions
+        uint32_t vg[32];
+        if (gated) tmem_ld32(trow + (BN >> 1) + c, vg);
+        tmem_ld_wait();
+        if (tre) p.trace[320 + (c >> 6) * 8 + 2] = clock64();
+        const f2 al2 = splat2(p.alpha);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          f2 f[4];
+          if (plain) {
+            const float4 ad0 = *reinterpret_cast<const float4*>(add + c + 8 * j);
+            const float4 ad1 = *reinterpret_cast<const float4*>(add + c + 8 * j + 4);
+            f[0] = f2{__uint_as_float(va[8 * j]) + ad0.x, __uint_as_float(va[8 * j + 1]) + ad0.y};
+            f[1] = f2{__uint_as_float(va[8 * j + 2]) + ad0.z, __uint_as_float(va[8 * j + 3]) + ad0.w};
+            f[2] = f2{__uint_as_float(va[8 * j + 4]) + ad1.x, __uint_as_float(va[8 * j + 5]) + ad1.y};
+            f[3] = f2{__uint_as_float(va[8 * j + 6]) + ad1.z, __uint_as_float(va[8 * j + 7]) + ad1.w};
+          } else {
+            const float4 ad0 = *reinterpret_cast<const float4*>(add + c + 8 * j);
+            const float4 ad1 = *reinterpret_cast<const float4*>(add + c + 8 * j + 4);
+            const f2 adp[4] = {f2{ad0.x, ad0.y}, f2{ad0.z, ad0.w}, f2{ad1.x, ad1.y}, f2{ad1.z, ad1.w}};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              f[k] = fma2(f2{__uint_as_float(va[8 * j + 2 * k]), __uint_as_float(va[8 * j + 2 * k + 1])}, al2, adp[k]);
+            if (gated) {
+              const float4 ag0 = *reinterpret_cast<const float4*>(add + (BN >> 1) + c + 8 * j);
+              const float4 ag1 = *reinterpret_cast<const float4*>(add + (BN >> 1) + c + 8 * j + 4);
+              const f2 agp[4] = {f2{ag0.x, ag0.y}, f2{ag0.z, ag0.w}, f2{ag1.x, ag1.y}, f2{ag1.z, ag1.w}};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                f2 g = fma2(f2{__uint_as_float(vg[8 * j + 2 * k]), __uint_as_float(vg[8 * j + 2 * k + 1])}, al2, agp[k]);
+                if (p.act == UR_ACT_GEGLU) g = gelu_erf2(g);
+                f[k] = mul2(f[k], g);
+              }
+            } else if (p.act == UR_ACT_SILU) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) f[k] = f2{silu_f(f[k].x), silu_f(f[k].y)};
+            } else if (p.act == UR_ACT_GELU) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) f[k] = gelu_erf2(f[k]);
+            }
+            if (has_mul) {
+              const float4 m0 = *reinterpret_cast<const float4*>(mul + c + 8 * j);
+              const float4 m1 = *reinterpret_cast<const float4*>(mul + c + 8 * j + 4);
+              f[0] = mul2(f[0], f2{m0.x, m0.y});
+              f[1] = mul2(f[1], f2{m0.z, m0.w});
+              f[2] = mul2(f[2], f2{m1.x, m1.y});
+              f[3] = mul2(f[3], f2{m1.z, m1.w});
+            }
+          }
+          // own row: (+ residual) -> bf16 -> staging (swizzled)
           uint4* sp = reinterpret_cast<uint4*>(stg + stg_off(r, j));
           if (p.residual) {
             const uint4 rv = *sp;
@@ -475,12 +496,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
             for (int k = 0; k < 4; ++k) {
               float a0, a1;
               unpack_bf16(u[k], a0, a1);
-              f[8 * j + 2 * k] += a0;
-              f[8 * j + 2 * k + 1] += a1;
+              f[k].x += a0;
+              f[k].y += a1;
             }
           }
-          *sp = make_uint4(pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                           pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+          *sp = make_uint4(pack_bf16(f[0].x, f[0].y), pack_bf16(f[1].x, f[1].y), pack_bf16(f[2].x, f[2].y),
+                           pack_bf16(f[3].x, f[3].y));
         }
         if (tre) p.trace[320 + (c >> 6) * 8 + 3] = clock64();
         if (use_tma) {
