@@ -108,7 +108,9 @@ int ur_debug_set_gemm_trace(void* buf);
 int ur_debug_set_gemm_pair_mode(int mode);
 /* Development: 0 disables split-K (ur_conv_desc.workspace is then ignored); returns the previous value. */
 int ur_debug_set_gemm_splitk(int on);
-/* Development: 0 = persistent-kernel epilogue stores with st.global instead of TMA; returns the previous value. */
+/* Development: persistent-kernel epilogue stores: 0 = st.global, 1 = one TMA store per 128-row sub-block (group
+ * barrier), 2 = one TMA store per epilogue warp (32-row boxes, no barrier on the store path; default); returns the
+ * previous value. */
 int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 /* Development: attention kernel generation for head_dim 64 / 128: 2 = attention2_kernel (default: one softmax thread per

@@ -285,3 +285,36 @@ def test_group_norm_uses_epilogue_statistics():
     c1 = ops.group_norm(y1, 32, g, be, 1e-5, x2=y2)
     c2 = ops.group_norm(y2, 32, g, be, 1e-5, x2=y2)
     assert_close(c1, c2, 2e-3, "concat group_norm with mixed statistics sources")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(2, 64, 64, 320, 320, 1), (3, 16, 16, 640, 640, 9), (8, 8, 8, 1280, 640, 1),
+                                                 (2, 20, 24, 128, 200, 9), (1, 1, 300, 320, 960, 1), (5, 4, 8, 128, 256, 1)])
+def test_epilogue_store_modes_agree(B, H, W, Cin, Cout, taps):
+    """The three store paths of the persistent kernel's epilogue -- st.global (0), one TMA store per 128-row sub-block
+    after a group barrier (1), one TMA store per epilogue warp with 32-row boxes and no barrier (2, default) -- produce
+    bit-identical outputs and statistics, with bias + residual + fused statistics, ragged tiles and 1/2/4 images per
+    tile."""
+    from unirestore_b200 import _cabi, ops
+    x = _rand(B, Cin, H, W, seed=130)
+    k = 3 if taps == 9 else 1
+    w = _rand(Cout, Cin, k, k, seed=131, scale=(taps * Cin) ** -0.5)
+    b = _rand(Cout, seed=132)
+    r = _rand(B, H, W, Cout, seed=133).to(torch.bfloat16)
+    xb, wp = _nhwc(x), ops.pack_conv_weight(w.to(torch.bfloat16))
+    outs = {}
+    for mode in (2, 1, 0):
+        old = _cabi.lib().ur_debug_set_gemm_tma_store(mode)
+        try:
+            y = ops.conv_gemm(xb, wp, Cout, taps=ops.TAPS_3x3 if taps == 9 else ops.TAPS_1x1, bias=b, residual=r,
+                              want_stats=True)
+            torch.cuda.synchronize()
+            outs[mode] = (y.clone(), y._ur_stats.clone())
+        finally:
+            _cabi.lib().ur_debug_set_gemm_tma_store(old)
+    ref = bf16_round(F.conv2d(xb.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=k // 2)
+                     .permute(0, 2, 3, 1) + r.float())
+    assert_close(outs[2][0], ref, TOL, "warp-store epilogue %s" % ((B, H, W, Cin, Cout, taps),))
+    for mode in (1, 0):
+        assert torch.equal(outs[mode][0], outs[2][0]), "store mode %d output differs from warp mode" % mode
+        scale = outs[2][1].abs().amax().clamp_min(1e-6)
+        assert ((outs[mode][1] - outs[2][1]).abs() / scale).max().item() < 1e-6

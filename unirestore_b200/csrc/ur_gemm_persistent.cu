@@ -306,6 +306,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     uint8_t* const stg_base = staging + grp * kEpiStageBytes;
     int sbuf = 0;                                 // staging buffer of the next sub-block (alternates)
     const bool use_tma = p.tma_store != 0;
+    // tma_store == 2 ("warp mode"): the output tensor map has a 32-row box and every epilogue WARP stores its own 32
+    // rows (= its TMEM lane quarter) as soon as it has written them: no barrier between the four warps of a group on
+    // the store path (the two 128-thread barriers per 32-column sub-block cost ~300 of its ~1 200 cycles, and the K <= 640
+    // linears / GEGLU layers are epilogue-bound).  The residual is then staged by the warp for its own rows, too.
+    const bool warp_mode = p.tma_store == 2;
+    const int wrow0 = q * 32;                     // first tile row of this warp
+    const int mrow0 = warp_mode ? wrow0 + (lane >> 2) : crow0;       // rows this thread moves: mrow0 + mstep * i
+    const int mstep = warp_mode ? 8 : 32;
+    const int mchunk = warp_mode ? (lane & 3) : cchunk;
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     // this thread's two columns (gt, gt + 128) of the NEXT tile's add / mul vectors (every warp group stages its own copy)
     float a_nx[2] = {0.f, 0.f}, m_nx[2] = {1.f, 1.f};
@@ -379,12 +388,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       long long roff[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int rr = crow0 + 32 * i;
+        const int rr = mrow0 + mstep * i;
         const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
         const int b = tc.b0 + (rr >> (p.wt_log2 + p.ht_log2));
         const bool ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
         roff[i] = ok ? (b * p.res_sb + y * p.res_sy + x * p.res_sx + nout0) : -1;
       }
+      // warp mode: output coordinates of this warp's first row (its 32 rows form one box of the output tensor map)
+      const int wx = tc.x0 + (wrow0 & (Wt - 1)), wy = tc.y0 + ((wrow0 >> p.wt_log2) & (Ht - 1));
+      const int wb = tc.b0 + (wrow0 >> (p.wt_log2 + p.ht_log2));
       auto ooff = [&](int i) {                    // output offset of cooperative row i (non-TMA store path only)
         const int rr = crow0 + 32 * i;
         const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
@@ -395,7 +407,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       uint4 rres[4];
       int c = ((grp + it) & 1) * 32;            // the groups alternate which one takes the odd sub-block out (balance)
       if (p.residual) {
-        const int col = c + cchunk * 8;
+        const int col = c + mchunk * 8;
         const bool okc = c < ncols && nout0 + col + 8 <= n_out;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -416,18 +428,23 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         uint32_t va[32];
         tmem_ld32(trow + c, va);
         // (A) this staging buffer is free again: the TMA store issued from it two sub-blocks ago has read it
-        if (use_tma && gt == 0) bulk_wait_group_read<1>();
-        group_barrier(2 + grp);
+        if (warp_mode) {
+          if (lane == 0) bulk_wait_group_read<1>();
+          __syncwarp();
+        } else {
+          if (use_tma && gt == 0) bulk_wait_group_read<1>();
+          group_barrier(2 + grp);
+        }
         if (tre) p.trace[320 + (c >> 6) * 8 + 1] = clock64();
         if (p.residual) {
           // park the prefetched (coalesced) residual chunk in the staging buffer
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(stg + stg_off(crow0 + 32 * i, cchunk)) = rres[i];
-          group_barrier(4 + grp);
+            *reinterpret_cast<uint4*>(stg + stg_off(mrow0 + mstep * i, mchunk)) = rres[i];
+          if (warp_mode) __syncwarp(); else group_barrier(4 + grp);
           // prefetch the residual of this group's next sub-block
           const int cn = c + 64;
-          const int col = cn + cchunk * 8;
+          const int col = cn + mchunk * 8;
           const bool okc = cn < ncols && nout0 + col + 8 <= n_out;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -504,7 +521,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
                            pack_bf16(f[3].x, f[3].y));
         }
         if (tre) p.trace[320 + (c >> 6) * 8 + 3] = clock64();
-        if (use_tma) {
+        if (warp_mode) {
+          // (C) one TMA store per warp and sub-block: box (32 ch, 32 rows of this warp), clipped against the tensor
+          fence_proxy_async_smem();                 // generic-proxy writes above -> visible to the async proxy
+          __syncwarp();
+          if (tre) p.trace[320 + (c >> 6) * 8 + 4] = clock64();
+          if (lane == 0) {
+            tma_store_4d(&mapOut, stg + wrow0 * 64, nout0 + c, wx, wy, wb);
+            bulk_commit_group();
+          }
+        } else if (use_tma) {
           // (C) one TMA store per sub-block: the box (32 ch, Wt, Ht, Bt) is clipped against the output tensor
           fence_proxy_async_smem();                 // generic-proxy writes above -> visible to the async proxy
           group_barrier(6 + grp);
@@ -597,7 +623,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       if constexpr (PAIR) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
       if (tracing && it < 8 && et == 0) p.trace[6 * 16 + it] = clock64();
     }
-    if (use_tma && gt == 0) bulk_wait_group_all();      // shared memory must outlive the last TMA stores
+    if (use_tma && (warp_mode ? lane == 0 : gt == 0)) bulk_wait_group_all();      // shared memory must outlive the last TMA stores
   }
 
   tc_fence_before();
