@@ -37,7 +37,7 @@ struct PCfg {
   static constexpr int kWRows = PAIR ? BN / 2 : BN;
   static constexpr int kWBytes = kWRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kWBytes;
-  static constexpr int kFixed = 2 * kEpiStageBytes + 8 * BN * 4 + 2 * 128 * 8 + 512;
+  static constexpr int kFixed = 2 * kEpiStageBytes + 8 * BN * 4 + 4 * 128 * 8 + 512;
   static constexpr int kFit = (227 * 1024 - kFixed) / kStageBytes;
   static constexpr int kStages = kFit > 8 ? 8 : kFit;
   static constexpr int kSmem = kStages * kStageBytes + kFixed;
@@ -79,8 +79,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   uint8_t* staging = smem + STAGES * kStageBytes;                          // [2 groups][128 x 80 B]
   float* s_add = reinterpret_cast<float*>(staging + 2 * kEpiStageBytes);    // [2 groups][2][BN] (a private copy per
   float* s_mul = s_add + 4 * BN;                                            //  warp group: the groups never sync)
-  float* s_stat = s_mul + 4 * BN;                                           // [2 groups][128] float2 (epilogue statistics)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + 2 * 128 * 2);
+  float* s_stat = s_mul + 4 * BN;                                           // [2 groups][2 buffers][128] float2 (epilogue statistics)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stat + 4 * 128 * 2);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
@@ -592,7 +592,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
               s2 = fmaf(v, v, s2);
             }
           }
-          float2* sred = reinterpret_cast<float2*>(s_stat) + grp * 128;
+          // (double-buffered by sub-block: without the store-path barriers a fast warp may write the next sub-block's
+          //  partials while warp 0 still reads these; the barrier of the sub-block in between orders the reuse)
+          float2* sred = reinterpret_cast<float2*>(s_stat) + (grp * 2 + sbuf) * 128;
           sred[gt] = make_float2(s1, s2);
           group_barrier(8 + grp);
           if (gt < 32) {
