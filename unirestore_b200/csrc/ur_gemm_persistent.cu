@@ -567,7 +567,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           //      takes column (gt & 31) over rows 32 * (gt >> 5) .. + 31 (one conflict-free 2-byte LDS per row; the
           //      swizzle only depends on (row >> 1) & 3, so four base pointers cover all rows); the four row quarters
           //      meet in shared memory and one warp adds them to the fp64 statistics of the image(s) of the tile
-          const int scol = gt & 31, sq4 = gt >> 5;
+          // (the quarter is the warp's OWN TMEM lane quarter q -- the rows its lanes just wrote -- not its position in
+          //  the group: group 0 is warps 6..9 = quarters 2, 3, 0, 1; reading another warp's rows needed the group barrier
+          //  that warp mode removed: racecheck r2c11)
+          const int scol = lane, sq4 = q;
           const uint8_t* sb0 = stg + sq4 * 32 * 64 + (scol & 7) * 2;
           const int ch = scol >> 3;
           const uint8_t* sbk[4] = {sb0 + ((ch ^ 0) << 4), sb0 + ((ch ^ 1) << 4), sb0 + ((ch ^ 2) << 4), sb0 + ((ch ^ 3) << 4)};
@@ -595,7 +598,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           // (double-buffered by sub-block: without the store-path barriers a fast warp may write the next sub-block's
           //  partials while warp 0 still reads these; the barrier of the sub-block in between orders the reuse)
           float2* sred = reinterpret_cast<float2*>(s_stat) + (grp * 2 + sbuf) * 128;
-          sred[gt] = make_float2(s1, s2);
+          sred[sq4 * 32 + scol] = make_float2(s1, s2);
           group_barrier(8 + grp);
           if (gt < 32) {
             // the four 32-row quarters belong to Bt = 1, 2 or 4 consecutive images (a quarter never spans two: the
