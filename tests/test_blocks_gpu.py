@@ -13,7 +13,8 @@ from tests.util import assert_close, bf16_round
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-TOL_BLOCK = 2e-2      # one block, bf16 activations vs fp32 oracle
+TOL_BLOCK = 7.5e-3    # one block, bf16 activations vs fp32 oracle: <= 2x the measured 2.4e-3..3.8e-3 (profiles/parity_r2.txt);
+                      # the gates at identical rounding points (<= 2e-3) live in test_parity_rounded_gpu.py
 DEV = "cuda:0"
 
 
@@ -165,7 +166,7 @@ def test_controller_golden():
     y = m(rnd(g["x_seed"], *g["x_shape"]).to(DEV), torch.tensor([g["t"]], device=DEV))
     assert set(y) == set(g["out"])
     for k in y:
-        assert_close(y[k], g["out"][k].to(DEV), 3e-2, "Controller[%d] vs reference golden" % k)
+        assert_close(y[k], g["out"][k].to(DEV), 2.2e-2, "Controller[%d] vs reference golden" % k)     # measured 6e-3..1.1e-2
 
 
 @pytest.mark.parametrize("B,H,W,C1,C2,G,silu", [(2, 16, 16, 320, 0, 32, True), (3, 8, 8, 1280, 1280, 32, True),

@@ -44,7 +44,7 @@ def test_controlled_unet_golden(model):
     control = {k: v.to(DEV) for k, v in c["out"].items()}
     zt = rnd(g["zt_seed"], *g["zt_shape"]).to(DEV)
     y = model.base_model(zt, control, torch.tensor([g["t"]], device=DEV))
-    assert_close(y, g["out"].to(DEV), 3e-2, "ControlledUNet vs reference golden")
+    assert_close(y, g["out"].to(DEV), 1.5e-2, "ControlledUNet vs reference golden")            # measured 7.4e-3
 
 
 def test_autoencoder_golden(model):
@@ -54,13 +54,13 @@ def test_autoencoder_golden(model):
     torch.manual_seed(g["rng_seed"])
     noise = torch.randn(1, 4, g["img_shape"][2] // 8, g["img_shape"][3] // 8).to(DEV)
     z, skips = model.ae.encode(img, enable_fr=True, noise=noise)
-    assert_close(z, g["z"].to(DEV), 3e-2, "encode z vs reference golden")
-    for i, s in enumerate(skips):
-        assert_close(s.float()[..., ::4, ::4], g["skips"][i]["sample"].to(DEV), 3e-2, "encode skip%d" % i)
+    assert_close(z, g["z"].to(DEV), 1.4e-2, "encode z vs reference golden")                   # measured 7.0e-3
+    for i, (s, tol) in enumerate(zip(skips, (1.5e-2, 2.2e-2, 3.6e-2))):                      # measured 7.3e-3 / 1.1e-2 / 1.8e-2
+        assert_close(s.float()[..., ::4, ::4], g["skips"][i]["sample"].to(DEV), tol, "encode skip%d" % i)
     # decode from the REFERENCE latents/skips is not possible (goldens keep sub-sampled skips): decode our own
     for task in ("ir", "seg"):
         y = model.ae.decode(z, skips, task)
-        assert_close(y, g["decode"][task].to(DEV), 5e-2, "decode[%s] vs reference golden" % task)
+        assert_close(y, g["decode"][task].to(DEV), 1.6e-2, "decode[%s] vs reference golden" % task)   # measured 7.8e-3
     with pytest.raises(KeyError):
         model.ae.decode(z, skips, "no-such-task")
 
@@ -74,7 +74,7 @@ def test_diffuie_forward_golden(model):
     assert model.scheduler.timesteps.tolist() == g["timesteps"].tolist()
     y = model(img, g["task"], noise=(n_post.to(DEV), n_diff.to(DEV)))
     assert y.shape == g["out"].shape
-    assert_close(y, g["out"].to(DEV), 1e-1, "DiffUIE.forward (2 DDIM steps, 512x640) vs reference golden")
+    assert_close(y, g["out"].to(DEV), 1e-2, "DiffUIE.forward (2 DDIM steps, 512x640) vs reference golden")   # measured 4.6e-3
 
 
 def test_diffuie_forward_small_input_vs_oracle(model):
@@ -92,7 +92,7 @@ def test_diffuie_forward_small_input_vs_oracle(model):
         ref = om(img, "seg", noise=(n_post, n_diff))
     y = model(img.to(DEV), "seg", noise=(n_post.to(DEV), n_diff.to(DEV)))
     assert y.shape == ref.shape == (1, 3, 200, 260)
-    assert_close(y, ref.to(DEV), 1e-1, "DiffUIE.forward (200x260 input: resize + reflect pad + crop + resize back) vs oracle")
+    assert_close(y, ref.to(DEV), 1e-2, "DiffUIE.forward (200x260 input: resize + reflect pad + crop + resize back) vs oracle")   # measured 4.6e-3
 
 
 def test_predict_z0_per_sample_timesteps_vs_oracle(model):
@@ -107,6 +107,6 @@ def test_predict_z0_per_sample_timesteps_vs_oracle(model):
         ref = om.predict_z0(zt, z0, ts)
         same = om.predict_z0(zt, z0, torch.tensor([749, 749, 749]))
     got = model.predict_z0(zt.to(DEV), z0.to(DEV), ts.to(DEV))
-    assert_close(got, ref.to(DEV), 5e-2, "predict_z0 with per-sample timesteps vs oracle")
+    assert_close(got, ref.to(DEV), 8e-3, "predict_z0 with per-sample timesteps vs oracle")       # measured 3.8e-3
     got1 = model.predict_z0(zt.to(DEV), z0.to(DEV), torch.tensor([749], device=DEV))
-    assert_close(got1, same.to(DEV), 5e-2, "predict_z0 with one shared timestep vs oracle")
+    assert_close(got1, same.to(DEV), 8e-3, "predict_z0 with one shared timestep vs oracle")

@@ -81,10 +81,10 @@ def test_config2_graph_multistream_vs_eager_vs_oracles(models):
     _log("config2 drift table: DDIM step | cuda vs rounded oracle | cuda vs fp32 oracle | rounded vs fp32 oracle (rel-L2 of the latents)")
     for i in range(20):
         _log("config2 drift step %2d  %.3e  %.3e  %.3e" % (i + 1, rel_l2(tr[i], tq[i]), rel_l2(tr[i], tf[i]), rel_l2(tq[i], tf[i])))
-    e_q = assert_close(y_graph, y_q, 2e-2, "config2 B=8 512x512 20 steps, graph path vs rounded oracle (image)")
-    e_f = assert_close(y_graph, y_f, 3e-2, "config2 B=8 512x512 20 steps, graph path vs fp32 oracle (image)")
+    e_q = assert_close(y_graph, y_q, 7.5e-3, "config2 B=8 512x512 20 steps, graph path vs rounded oracle (image)")   # measured 3.6e-3
+    e_f = assert_close(y_graph, y_f, 9e-3, "config2 B=8 512x512 20 steps, graph path vs fp32 oracle (image)")        # measured 4.5e-3
     _log("config2 rounded oracle vs fp32 oracle (image) rel-L2 %.3e (the bf16-storage distance itself)" % rel_l2(y_q, y_f))
-    assert_close(tr[-1], tq[-1], 3e-2, "config2 final latents vs rounded oracle")
+    assert_close(tr[-1], tq[-1], 4e-3, "config2 final latents vs rounded oracle")                # measured 2.0e-3
     assert e_q <= e_f * 1.5 + 1e-3
 
 

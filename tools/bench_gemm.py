@@ -28,9 +28,9 @@ for name in a.shapes.split(","):
     taps = ops.TAPS_3x3 if nt == 9 else ops.TAPS_1x1
     out = torch.empty(B, H, W, Co, device=dev, dtype=torch.bfloat16)
     res = {}
-    for v1 in (0, 1, 2):      # 0: auto (CTA pairs when the cost model says so), 1: v1 kernel, 2: persistent single-CTA
+    for v1 in (0, 1, 2, 3):   # 0: auto (CTA pairs when the cost model says so), 1: v1 kernel, 2: persistent single-CTA, 3: forced pairs
         _cabi.lib().ur_debug_force_gemm_v1(1 if v1 == 1 else 0)
-        _cabi.lib().ur_debug_set_gemm_pair_mode(0 if v1 == 2 else -1)
+        _cabi.lib().ur_debug_set_gemm_pair_mode(0 if v1 == 2 else (1 if v1 == 3 else -1))
         for _ in range(3):
             ops.conv_gemm(x, w, Co, taps=taps, bias=bias, out=out)
         ts = []
@@ -50,6 +50,6 @@ for name in a.shapes.split(","):
     fl = 2.0 * B * H * W * Ci * Co * nt
     by = 2.0 * (B * H * W * (Ci + Co) + Co * nt * Ci)
     t = res[0]
-    print("%-20s auto %8.1f us %7.1f TF/s %6.0f GB/s | 1-CTA persistent %8.1f us %7.1f TF/s | v1 %8.1f us %7.1f TF/s" % (
-        name, t * 1e6, fl / t / 1e12, by / t / 1e9, res[2] * 1e6, fl / res[2] / 1e12, res[1] * 1e6, fl / res[1] / 1e12),
-        flush=True)
+    print("%-20s auto %8.1f us %7.1f TF/s %6.0f GB/s | 1-CTA persistent %8.1f us %7.1f TF/s | forced pairs %8.1f us %7.1f TF/s | v1 %8.1f us %7.1f TF/s" % (
+        name, t * 1e6, fl / t / 1e12, by / t / 1e9, res[2] * 1e6, fl / res[2] / 1e12, res[3] * 1e6, fl / res[3] / 1e12,
+        res[1] * 1e6, fl / res[1] / 1e12), flush=True)
