@@ -194,7 +194,7 @@ def test_forward_1024_vs_oracles():
         torch.cuda.empty_cache()
         with R.exact():
             y_f = R.forward(o, img, "ir", noise=noise)
-    assert_close(y, y_q, 1.2e-2, "1024x1024 B=1 2 steps, graph path vs rounded oracle (image)")
-    assert_close(y, y_f, 1.5e-2, "1024x1024 B=1 2 steps, graph path vs fp32 oracle (image)")
+    assert_close(y, y_q, 8e-3, "1024x1024 B=1 2 steps, graph path vs rounded oracle (image)")      # measured 4.1e-3
+    assert_close(y, y_f, 9e-3, "1024x1024 B=1 2 steps, graph path vs fp32 oracle (image)")         # measured 4.7e-3
     del o, m
     torch.cuda.empty_cache()
