@@ -115,7 +115,8 @@ int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 /* Development: attention kernel generation for head_dim 64 / 128: 2 = attention2_kernel (default: one softmax thread per
  * row, two query tiles per CTA, single TMEM pass, exp2 partly on the FMA pipe), 3 = attention3_kernel (the same CTA with two
- * softmax threads per row), 1 = first-generation kernel; returns the previous value. */
+ * softmax threads per row), 4 = attention4_kernel (head_dim 64: 64-key sub-tiles, double-buffered S / P, S prefetched into
+ * registers), 1 = first-generation kernel; returns the previous value. */
 int ur_debug_set_attention_impl(int impl);
 /* Development: how many of every 8 exponential pairs attention2 / attention3 evaluate with the FMA-pipe polynomial
  * instead of MUFU.EX2 (0..3); returns the previous value. */
