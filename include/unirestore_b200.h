@@ -113,12 +113,12 @@ int ur_debug_set_gemm_splitk(int on);
  * previous value. */
 int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
-/* Development: attention kernel generation for head_dim 64 / 128: 2 = attention2_kernel (default: one softmax thread per
- * row, two query tiles per CTA, single TMEM pass, exp2 partly on the FMA pipe), 3 = attention3_kernel (the same CTA with two
- * softmax threads per row), 4 = attention4_kernel (head_dim 64: 64-key sub-tiles, double-buffered S / P, S prefetched into
- * registers), 1 = first-generation kernel; returns the previous value. */
+/* Development: attention kernel generation for head_dim 64 / 128: 1 = attention_kernel (default: two softmax threads per
+ * row, two CTAs per SM), 2 = attention2_kernel (two query tiles per CTA, one softmax thread per row, single TMEM pass, P in
+ * tensor memory, exp2 partly on the FMA pipe; measured equal, profiles/attention_experiments_r2.txt); returns the previous
+ * value. */
 int ur_debug_set_attention_impl(int impl);
-/* Development: how many of every 8 exponential pairs attention2 / attention3 evaluate with the FMA-pipe polynomial
+/* Development: how many of every 8 exponential pairs attention2_kernel evaluates with the FMA-pipe polynomial
  * instead of MUFU.EX2 (0..3); returns the previous value. */
 int ur_debug_set_attention_poly(int n);
 

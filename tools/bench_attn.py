@@ -11,8 +11,8 @@ from unirestore_b200 import ops  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--cases", default="self64,self32,cross64,ctrl64")
-ap.add_argument("--poly", type=int, default=3, help="exp2 pairs of every 8 on the FMA pipe (attention2 / 3)")
-ap.add_argument("--impl", type=int, default=2, help="attention kernel generation (1, 2 or 3)")
+ap.add_argument("--poly", type=int, default=3, help="exp2 pairs of every 8 on the FMA pipe (attention2)")
+ap.add_argument("--impl", type=int, default=2, help="attention kernel generation (1 or 2)")
 a = ap.parse_args()
 from unirestore_b200 import _cabi  # noqa: E402
 _cabi.lib().ur_debug_set_attention_impl(a.impl)

@@ -901,659 +901,6 @@ static int launch_attention512(const AttnParams& p, const CUtensorMap& mq, const
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention512 launch");
 }
 
-// =====================================================================================================================
-// attention3_kernel: attention2_kernel's CTA (two 128-query tiles, shared K/V ring, S / O / P in tensor memory) with TWO
-// softmax threads per query row = 16 softmax warps per SM.
-//   ncu (gpurun_out/ncu_r2_attn*_self64, profiles/ncu_r2_attention.txt) showed attention_kernel stalled on memory
-//   instructions (two TMEM passes over S, P stores with 5 M shared-memory bank conflicts, a shared atomic per tile:
-//   long_scoreboard 2.4 / mio_throttle 1.8 per issue) and attention2_kernel on ALU dependencies with only two softmax
-//   warps per scheduler (stall_wait 33 %, issue slots 52 % busy).  Here four softmax warps per scheduler hide the ALU
-//   latencies and the memory stalls are gone:
-//     - ONE TMEM pass: a thread loads its 64 scores once; s_empty is released right after;
-//     - the tile maximum of the two half-row threads is exchanged through a double-buffered shared slot with plain stores
-//       (slot j & 1: the partner's store for tile j + 2 is ordered after barrier j + 1, my read of tile j before it) --
-//       no atomics; the running maximum lives in registers and is identical in both threads;
-//     - P goes to tensor memory (tcgen05.st) and P V reads its A operand from TMEM;
-//     - packed f32x2 scale / sum, 3-input max, kPolyOf8 of every 8 exponential pairs on the FMA pipe.
-//   Registers: warp group 0 (TMA, MMA, two idle warps) shrinks to 40, the softmax warp groups grow to 104.
-// =====================================================================================================================
-template <int D, int NQ>
-struct Attn3Cfg {
-  static constexpr int kStages = D == 64 ? 4 : 2;
-  static constexpr int kQBytes = kTileQ * D * 2;
-  static constexpr int kKBytes = kTileK * D * 2;
-  static constexpr int kSmem = NQ * kQBytes + kStages * 2 * kKBytes + 256 + NQ * 768 * 4 + 1024;
-  static constexpr int kThreads = (4 + 8 * NQ) * 32;
-  static constexpr int kColO = NQ * 128, kColP = NQ * 128 + NQ * D;
-  static_assert(kColP + NQ * 64 <= 512, "tensor memory budget");
-};
-
-template <int D, int NQ, int POLY>
-__global__ void __launch_bounds__(Attn3Cfg<D, NQ>::kThreads, 1)
-attention3_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
-                  const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
-  using Cfg = Attn3Cfg<D, NQ>;
-  constexpr int ND = D / 64;
-  constexpr int DH = D / 2;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kQBytes = Cfg::kQBytes, kKBytes = Cfg::kKBytes;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + NQ * kQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * 2 * kKBytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = q_full + 1;                       // [kStages]
-  uint64_t* kv_empty = kv_full + kStages;               // [kStages]
-  uint64_t* s_full = kv_empty + kStages;                // [NQ]
-  uint64_t* s_empty = s_full + NQ;                      // [NQ]
-  uint64_t* p_full = s_empty + NQ;                      // [NQ]
-  uint64_t* o_full = p_full + NQ;                       // [NQ]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + NQ);
-  float* xch_all = reinterpret_cast<float*>(bars + 32);  // [NQ][768]: 2 slots x 2 halves x 128 tile maxima, 2 x 128 row sums
-
-  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
-  const int q_base = blockIdx.x * (kTileQ * NQ);
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = (p.Tk + kTileK - 1) / kTileK;
-  const int nq_act = (NQ == 2 && q_base + kTileQ < p.Tq) ? 2 : 1;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapK);
-    tma_prefetch_desc(&mapV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int x = 0; x < NQ; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&s_empty[x], 256);
-      mbar_init(&p_full[x], 256);
-      mbar_init(&o_full[x], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_launch_dependents();
-  pdl_wait();
-  if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (elect_one_sync()) {
-      mbar_expect_tx(q_full, nq_act * kQBytes);
-      for (int x = 0; x < nq_act; ++x)
-#pragma unroll
-        for (int nb = 0; nb < ND; ++nb)
-          tma_load_3d(sQ + x * kQBytes + nb * (kTileQ * 128), &mapQ, q_full, h * D + nb * 64, q_base + x * kTileQ, b);
-    }
-    __syncwarp();
-    const int bk = p.kv_shared ? 0 : b;
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % kStages;
-      mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
-      uint8_t* sk = sKV + s * 2 * kKBytes;
-      if (elect_one_sync()) {
-        mbar_expect_tx(&kv_full[s], 2 * kKBytes);
-#pragma unroll
-        for (int nb = 0; nb < ND; ++nb) {
-          tma_load_3d(sk + nb * (kTileK * 128), &mapK, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
-          tma_load_3d(sk + kKBytes + nb * (kTileK * 128), &mapV, &kv_full[s], h * D + nb * 64, j * kTileK, bk);
-        }
-      }
-      __syncwarp();
-    }
-   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
-    const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
-    mbar_wait(q_full, 0);
-    auto issue_s = [&](int x, int j) {
-      const int s = j % kStages;
-      if (x == 0) mbar_wait(&kv_full[s], (j / kStages) & 1);
-      tc_fence_after();
-      const uint32_t aK = aKV + s * 2 * kKBytes;
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int nb = 0; nb < ND; ++nb)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_bf16(tmem_base + x * 128, umma_desc_k_sw128(aQ + x * kQBytes + nb * (kTileQ * 128)) + 2 * k,
-                        umma_desc_k_sw128(aK + nb * (kTileK * 128)) + 2 * k, idesc_s, (nb | k) != 0 ? 1u : 0u);
-        tc_commit(&s_full[x]);
-      }
-      __syncwarp();
-    };
-    for (int x = 0; x < nq_act; ++x) issue_s(x, 0);
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % kStages;
-      const uint32_t aV = aKV + s * 2 * kKBytes + kKBytes;
-      const int kvalid = min(kTileK, p.Tk - j * kTileK);
-      const int nk16 = ((kvalid + 31) >> 5) << 1;
-      for (int x = 0; x < nq_act; ++x) {
-        const bool trm = p.trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= 4 && j < 8;
-        long long* tq = p.trace + 64 + (x * 4 + (j - 4)) * 8;
-        if (trm) tq[0] = clock64();
-        mbar_wait(&s_empty[x], j & 1);          // every softmax thread of tile x holds its part of S_x(j) in registers
-        if (trm) tq[1] = clock64();
-        if (j + 1 < nkv) issue_s(x, j + 1);     // runs under the softmax of tile j
-        if (trm) tq[2] = clock64();
-        mbar_wait(&p_full[x], j & 1);           // P_x(j) in tensor memory, O_x rescaled if it had to be
-        if (trm) tq[3] = clock64();
-        tc_fence_after();
-        if (elect_one_sync()) {
-#pragma unroll
-          for (int nb = 0; nb < ND; ++nb) {
-            for (int k = 0; k < nk16; ++k) {
-              const uint64_t db = umma_desc_mn_sw128(aV + nb * (kTileK * 128) + k * 16 * 128, kTileK * 128);
-              tc_mma_bf16_ts(tmem_base + Cfg::kColO + x * D + nb * 64, tmem_base + Cfg::kColP + x * 64 + 8 * k, db,
-                             idesc_pv, (j | k) != 0 ? 1u : 0u);
-            }
-          }
-          tc_commit(&o_full[x]);
-          if (x == nq_act - 1) tc_commit(&kv_empty[s]);
-        }
-        __syncwarp();
-        if (trm) tq[4] = clock64();
-      }
-    }
-   }
-  } else {
-    // setmaxnreg.inc only draws on registers released by setmaxnreg.dec INSIDE this CTA (the per-CTA pool): the kernel
-    // launches with 96 registers per thread (640 threads; 160 with 384), warp group 0 releases 128 x (96 - 40) = 7 168,
-    // so the 512 softmax threads can grow by at most 14 -> 104.  (Asking for 112 blocks forever: r2 call 6.)
-    if constexpr (NQ == 2) {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
-    }
-    // =============================== softmax / output: TWO threads per query row ===============================
-    // tile x: warps 4 + 8x .. 11 + 8x; warp w and w + 4 of a tile share a TMEM lane quarter; thread (row r, half hf) owns
-    // score columns / keys [64 hf, 64 hf + 64) and output columns [DH hf, DH hf + DH)
-    const int x = (warp - 4) >> 3;
-    const int hf = ((warp - 4) >> 2) & 1;
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;
-    if (x < nq_act) {
-      const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
-      const uint32_t tS = tmem_base + lane_off + x * 128 + hf * 64;
-      const uint32_t tO = tmem_base + lane_off + Cfg::kColO + x * D + hf * DH;
-      const uint32_t tP = tmem_base + lane_off + Cfg::kColP + x * 64 + hf * 32;     // 64 keys = 32 columns of bf16 pairs
-      float* xch = xch_all + x * 768;
-      const float sc = p.scale_log2;
-      float m = -INFINITY, mrun = -INFINITY, l0 = 0.f, l1 = 0.f;
-      for (int j = 0; j < nkv; ++j) {
-        const int kvalid = p.Tk - j * kTileK - hf * 64;       // keys of this thread's half that exist (may be <= 0)
-        const int nchunk = kvalid >= 64 ? 2 : (kvalid <= 0 ? 0 : ((kvalid + 31) >> 5));
-        const bool trs = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && r == 0 && hf == 0 && j >= 4 && j < 8;
-        long long* tp = p.trace + (x * 4 + (j - 4)) * 8;
-        if (trs) tp[0] = clock64();
-        mbar_wait(&s_full[x], j & 1);
-        if (trs) tp[1] = clock64();
-        tc_fence_after();
-        uint32_t v[2][32];
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          if (c < nchunk) tmem_ld32(tS + c * 32, v[c]);
-        tmem_ld_wait();
-        if (trs) tp[2] = clock64();
-        tc_fence_before();
-        mbar_arrive(&s_empty[x]);
-        if (kvalid < 64) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kvalid && c < nchunk) v[c][i] = __float_as_uint(-INFINITY);
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < nchunk) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = max3(mx0, __uint_as_float(v[c][i]), __uint_as_float(v[c][i + 1]));
-              mx1 = max3(mx1, __uint_as_float(v[c][i + 2]), __uint_as_float(v[c][i + 3]));
-            }
-          }
-        }
-        // tile maximum of the whole row: own half <-> partner half through the double-buffered slot
-        float* slot = xch + (j & 1) * 256;
-        slot[hf * 128 + r] = fmaxf(mx0, mx1);
-        asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
-        mrun = max3(mrun, slot[r], slot[128 + r]);
-        if (trs) tp[3] = clock64();
-        const float mxl = mrun * sc;
-        const bool need = (j == 0) || (mxl - m > 8.0f);        // identical in both threads of the row
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? exp2_approx(m - mxl) : 1.0f;
-          if (j > 0) {
-            mbar_wait(&o_full[x], (j - 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < DH / 32; ++c) {
-              uint32_t t0[32];
-              tmem_ld32(tO + c * 32, t0);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * alpha);
-              tmem_st32(tO + c * 32, t0);
-            }
-            tmem_st_wait();
-            l0 *= alpha;
-            l1 *= alpha;
-          }
-          if (need) m = mxl;
-        } else if (j > 0) {
-          mbar_wait(&o_full[x], (j - 1) & 1);    // P(j-1) V(j-1) has consumed the P columns this tile overwrites
-        }
-        if (trs) tp[4] = clock64();
-        const float nm = -m;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < nchunk) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a0, a1, e0, e1;
-              fma2(a0, a1, __uint_as_float(v[c][2 * i]), __uint_as_float(v[c][2 * i + 1]), sc, nm);
-              if ((i & 7) < POLY) {
-                exp2_poly2(e0, e1, a0, a1);
-              } else {
-                e0 = exp2_approx(a0);
-                e1 = exp2_approx(a1);
-              }
-              add2(l0, l1, l0, l1, e0, e1);
-              pk[i] = pack_bf16(e0, e1);
-            }
-            tmem_st16(tP + c * 16, pk);
-          }
-        }
-        if (trs) tp[5] = clock64();
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[x]);
-        if (trs) tp[6] = clock64();
-      }
-      // ---- last tile's P V, combine the two partial row sums, normalise, store
-      mbar_wait(&o_full[x], (nkv - 1) & 1);
-      tc_fence_after();
-      float* lsum = xch + 512;                                 // [2][128]
-      lsum[hf * 128 + r] = l0 + l1;
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + x) : "memory");
-      const float inv = 1.f / (lsum[r] + lsum[128 + r]);
-      const int q = q_base + x * kTileQ + r;
-      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D + hf * DH;
-#pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t t0[32];
-        tmem_ld32(tO + c * 32, t0);
-        tmem_ld_wait();
-        if (q < p.Tq) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(t0[8 * i]) * inv, __uint_as_float(t0[8 * i + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(t0[8 * i + 2]) * inv, __uint_as_float(t0[8 * i + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(t0[8 * i + 4]) * inv, __uint_as_float(t0[8 * i + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(t0[8 * i + 6]) * inv, __uint_as_float(t0[8 * i + 7]) * inv);
-            reinterpret_cast<uint4*>(op + c * 32)[i] = o;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-template <int D, int NQ, int POLY>
-static int launch_attention3(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                             cudaStream_t stream) {
-  using Cfg = Attn3Cfg<D, NQ>;
-  static_assert(Cfg::kSmem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention3_kernel<D, NQ, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention3)");
-    configured = true;
-  }
-  dim3 grid((p.Tq + kTileQ * NQ - 1) / (kTileQ * NQ), p.heads, p.batch);
-  cudaError_t e = launch_kernel(attention3_kernel<D, NQ, POLY>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
-  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention3 launch");
-}
-
-// =====================================================================================================================
-// attention4_kernel (head_dim 64): attention2_kernel's CTA (two 128-query tiles, one softmax thread per row, P in tensor
-// memory, shared 4-stage K/V ring) re-pipelined at 64-KEY SUB-TILES with DOUBLE-BUFFERED S and P per query tile:
-//     TMEM per query tile: S0 64 + S1 64 + P0 32 + P1 32 + O 64 = 256 columns (512 for the two tiles).
-//   The timeline of generations 2 / 3 (profiles/attention_experiments_r2.txt) showed ~1 100 cycles per KV tile and
-//   softmax group that are neither MUFU nor FMA work -- load S from TMEM, row maximum, waits and publishes -- strictly in
-//   series with the exponentials.  Here
-//     - the tensor core runs S two sub-tiles ahead (S(i+2) is issued right after P(i) V(i)), so a softmax thread never
-//       waits for scores;
-//     - the thread issues the TMEM load of sub-tile i+1 into a second register set BEFORE it starts the exponentials of
-//       sub-tile i (software prefetch), so the load latency hides under its own arithmetic;
-//     - P(i) V(i) starts after 64 keys instead of 128 and P is double-buffered, so the wait for the previous P V is off
-//       the path.
-//   Arithmetic, lazy rescaling and rounding points are those of attention2_kernel (per 64-key sub-tile).
-// =====================================================================================================================
-struct Attn4Cfg {
-  static constexpr int kStages = 4;
-  static constexpr int kQBytes = kTileQ * 64 * 2;
-  static constexpr int kKBytes = kTileK * 64 * 2;
-  static constexpr int kSmem = 2 * kQBytes + kStages * 2 * kKBytes + 1024;
-  static constexpr int kThreads = 12 * 32;
-};
-
-template <int POLY>
-__global__ void __launch_bounds__(Attn4Cfg::kThreads, 1)
-attention4_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
-                  const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV) {
-  using Cfg = Attn4Cfg;
-  constexpr int D = 64, NQ = 2, kSub = 64;
-  constexpr int kStages = Cfg::kStages;
-  constexpr int kQBytes = Cfg::kQBytes, kKBytes = Cfg::kKBytes;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + NQ * kQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kStages * 2 * kKBytes);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = q_full + 1;                       // [kStages]
-  uint64_t* kv_empty = kv_full + kStages;               // [kStages]
-  uint64_t* s_full = kv_empty + kStages;                // [NQ][2]
-  uint64_t* s_empty = s_full + 4;                       // [NQ][2]
-  uint64_t* p_full = s_empty + 4;                       // [NQ][2]
-  uint64_t* pv_done = p_full + 4;                       // [NQ][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
-
-  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
-  const int q_base = blockIdx.x * (kTileQ * NQ);
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = (p.Tk + kTileK - 1) / kTileK;
-  const int nsub = (p.Tk + kSub - 1) / kSub;
-  const int nq_act = (q_base + kTileQ < p.Tq) ? 2 : 1;
-
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&mapQ);
-    tma_prefetch_desc(&mapK);
-    tma_prefetch_desc(&mapV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&pv_done[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = warp_uniform(*tmem_slot);
-  pdl_launch_dependents();
-  pdl_wait();
-  // TMEM columns of query tile x: S buffer u at 256 x + 64 u, P buffer u at 256 x + 128 + 32 u, O at 256 x + 192
-  if (warp < 4) {
-   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (elect_one_sync()) {
-      mbar_expect_tx(q_full, nq_act * kQBytes);
-      for (int x = 0; x < nq_act; ++x) tma_load_3d(sQ + x * kQBytes, &mapQ, q_full, h * D, q_base + x * kTileQ, b);
-    }
-    __syncwarp();
-    const int bk = p.kv_shared ? 0 : b;
-    for (int j = 0; j < nkv; ++j) {
-      const int s = j % kStages;
-      mbar_wait(&kv_empty[s], ((j / kStages) & 1) ^ 1);
-      uint8_t* sk = sKV + s * 2 * kKBytes;
-      if (elect_one_sync()) {
-        mbar_expect_tx(&kv_full[s], 2 * kKBytes);
-        tma_load_3d(sk, &mapK, &kv_full[s], h * D, j * kTileK, bk);
-        tma_load_3d(sk + kKBytes, &mapV, &kv_full[s], h * D, j * kTileK, bk);
-      }
-      __syncwarp();
-    }
-   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
-    const uint32_t aQ = smem_u32(sQ), aKV = smem_u32(sKV);
-    mbar_wait(q_full, 0);
-    auto issue_s = [&](int x, int i) {          // S_x(i) = Q_x K[64 i .. 64 i + 64)^T -> S buffer i & 1 of tile x
-      const int u = i & 1, j = i >> 1, s = j % kStages;
-      if (x == 0 && u == 0) mbar_wait(&kv_full[s], (j / kStages) & 1);       // first touch of KV tile j
-      tc_fence_after();
-      const uint32_t aK = aKV + s * 2 * kKBytes + u * (kSub * 128);
-      if (elect_one_sync()) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_bf16(tmem_base + x * 256 + u * 64, umma_desc_k_sw128(aQ + x * kQBytes) + 2 * k,
-                      umma_desc_k_sw128(aK) + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        tc_commit(&s_full[x * 2 + u]);
-      }
-      __syncwarp();
-    };
-    // S runs ahead of the softmax: S(0), S(1) at once, S(i+3) as soon as the softmax holds S(i+1) in registers (its
-    // buffer is then free), i.e. a full sub-tile before the thread prefetches it
-    for (int i = 0; i < 2 && i < nsub; ++i)
-      for (int x = 0; x < nq_act; ++x) issue_s(x, i);
-    if (nsub > 2)
-      for (int x = 0; x < nq_act; ++x) {
-        mbar_wait(&s_empty[x * 2], 0);                    // S_x(0) is in registers (softmax prologue)
-        issue_s(x, 2);
-      }
-    for (int i = 0; i < nsub; ++i) {
-      const int u = i & 1, j = i >> 1, s = j % kStages;
-      const uint32_t aV = aKV + s * 2 * kKBytes + kKBytes + u * (kSub * 128);
-      const int kvalid = min(kSub, p.Tk - i * kSub);
-      const int nk16 = ((kvalid + 31) >> 5) << 1;
-      const bool last_of_tile = (u == 1) || (i == nsub - 1);
-      for (int x = 0; x < nq_act; ++x) {
-        mbar_wait(&p_full[x * 2 + u], (i >> 1) & 1);      // P_x(i) in tensor memory, O_x rescaled if it had to be
-        tc_fence_after();
-        if (elect_one_sync()) {
-          for (int k = 0; k < nk16; ++k) {
-            const uint64_t db = umma_desc_mn_sw128(aV + k * 16 * 128, kTileK * 128);
-            tc_mma_bf16_ts(tmem_base + x * 256 + 192, tmem_base + x * 256 + 128 + u * 32 + 8 * k, db, idesc_pv,
-                           (i | k) != 0 ? 1u : 0u);
-          }
-          tc_commit(&pv_done[x * 2 + u]);
-          if (x == nq_act - 1 && last_of_tile) tc_commit(&kv_empty[s]);
-        }
-        __syncwarp();
-        if (i + 3 < nsub) {
-          mbar_wait(&s_empty[x * 2 + (u ^ 1)], ((i + 1) >> 1) & 1);    // S_x(i+1) is in registers: buffer (i+1)&1 is free
-          issue_s(x, i + 3);
-        }
-      }
-    }
-   }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
-    // =============================== softmax / output: one thread per query row ===============================
-    const int x = (warp - 4) >> 2;
-    const int qd = warp & 3;
-    const int r = qd * 32 + lane;
-    if (x < nq_act) {
-      const uint32_t tl = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + x * 256;
-      const uint32_t tO = tl + 192;
-      const float sc = p.scale_log2;
-      float m = -INFINITY, mrun = -INFINITY, l0 = 0.f, l1 = 0.f;
-      uint32_t bufA[2][32], bufB[2][32];
-      // one 64-key sub-tile: `cur` holds its scores, `nxt` receives the next sub-tile's while this one is processed
-      auto step = [&](int i, uint32_t (&cur)[2][32], uint32_t (&nxt)[2][32]) {
-        const int u = i & 1;
-        const bool has_next = i + 1 < nsub;
-        const int kvalid = p.Tk - i * kSub;
-        const int nchunk = kvalid >= kSub ? 2 : ((kvalid + 31) >> 5);
-        if (has_next) {                                   // prefetch S(i+1) into the other register set
-          const int kv_n = p.Tk - (i + 1) * kSub;
-          mbar_wait(&s_full[x * 2 + (u ^ 1)], ((i + 1) >> 1) & 1);
-          tc_fence_after();
-          tmem_ld32(tl + (u ^ 1) * 64, nxt[0]);
-          if (kv_n > 32) tmem_ld32(tl + (u ^ 1) * 64 + 32, nxt[1]);
-        }
-        if (kvalid < kSub) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int k = 0; k < 32; ++k)
-              if (c * 32 + k >= kvalid && c < nchunk) cur[c][k] = __float_as_uint(-INFINITY);
-        }
-        float mx0 = mrun, mx1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < nchunk) {
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              mx0 = max3(mx0, __uint_as_float(cur[c][k]), __uint_as_float(cur[c][k + 1]));
-              mx1 = max3(mx1, __uint_as_float(cur[c][k + 2]), __uint_as_float(cur[c][k + 3]));
-            }
-          }
-        }
-        mrun = fmaxf(mx0, mx1);
-        const float mxl = mrun * sc;
-        const bool need = (i == 0) || (mxl - m > 8.0f);
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? exp2_approx(m - mxl) : 1.0f;
-          if (i > 0) {
-            mbar_wait(&pv_done[x * 2 + (u ^ 1)], ((i - 1) >> 1) & 1);      // every P V up to sub-tile i-1 has landed
-            tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t t0[32];
-              tmem_ld32(tO + c * 32, t0);
-              tmem_ld_wait();                             // (also completes the prefetch loads: harmless)
-#pragma unroll
-              for (int k = 0; k < 32; ++k) t0[k] = __float_as_uint(__uint_as_float(t0[k]) * alpha);
-              tmem_st32(tO + c * 32, t0);
-            }
-            tmem_st_wait();
-            l0 *= alpha;
-            l1 *= alpha;
-          }
-          if (need) m = mxl;
-        }
-        const float nm = -m;
-        if (i >= 2) mbar_wait(&pv_done[x * 2 + u], ((i - 2) >> 1) & 1);      // P buffer u is free again (long since)
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c < nchunk) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              float a0, a1, e0, e1;
-              fma2(a0, a1, __uint_as_float(cur[c][2 * k]), __uint_as_float(cur[c][2 * k + 1]), sc, nm);
-              if ((k & 7) < POLY) {
-                exp2_poly2(e0, e1, a0, a1);
-              } else {
-                e0 = exp2_approx(a0);
-                e1 = exp2_approx(a1);
-              }
-              add2(l0, l1, l0, l1, e0, e1);
-              pk[k] = pack_bf16(e0, e1);
-            }
-            tmem_st16(tl + 128 + u * 32 + c * 16, pk);
-          }
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[x * 2 + u]);
-        if (has_next) {                                   // S(i+1) is in registers: its TMEM buffer may be overwritten
-          tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&s_empty[x * 2 + (u ^ 1)]);
-        }
-      };
-      // prologue: sub-tile 0 into bufA
-      mbar_wait(&s_full[x * 2], 0);
-      tc_fence_after();
-      tmem_ld32(tl, bufA[0]);
-      if (p.Tk > 32) tmem_ld32(tl + 32, bufA[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_empty[x * 2]);
-      for (int i = 0; i < nsub; i += 2) {
-        step(i, bufA, bufB);
-        if (i + 1 < nsub) step(i + 1, bufB, bufA);
-      }
-      // ---- last P V, normalise, store
-      mbar_wait(&pv_done[x * 2 + ((nsub - 1) & 1)], ((nsub - 1) >> 1) & 1);
-      tc_fence_after();
-      const int q = q_base + x * kTileQ + r;
-      const float inv = 1.f / (l0 + l1);
-      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t t0[32];
-        tmem_ld32(tO + c * 32, t0);
-        tmem_ld_wait();
-        if (q < p.Tq) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(t0[8 * k]) * inv, __uint_as_float(t0[8 * k + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(t0[8 * k + 2]) * inv, __uint_as_float(t0[8 * k + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(t0[8 * k + 4]) * inv, __uint_as_float(t0[8 * k + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(t0[8 * k + 6]) * inv, __uint_as_float(t0[8 * k + 7]) * inv);
-            reinterpret_cast<uint4*>(op + c * 32)[k] = o;
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-template <int POLY>
-static int launch_attention4(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                             cudaStream_t stream) {
-  using Cfg = Attn4Cfg;
-  static_assert(Cfg::kSmem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention4_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
-    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention4)");
-    configured = true;
-  }
-  dim3 grid((p.Tq + kTileQ * 2 - 1) / (kTileQ * 2), p.heads, p.batch);
-  cudaError_t e = launch_kernel(attention4_kernel<POLY>, grid, dim3(Cfg::kThreads), Cfg::kSmem, stream, p, mq, mk, mv);
-  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention4 launch");
-}
-
 template <int D>
 static int launch_attention(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                             dim3 grid, cudaStream_t stream) {
@@ -1583,7 +930,7 @@ using namespace ur;
 static long long* g_attn_trace = nullptr;
 static int g_attn_impl = 1;      // 1: attention_kernel (default: measured faster, r2c2); 2: attention2_kernel
 static int g_attn_poly = kPolyOf8Default;
-// development: exponential pairs (of every 8) evaluated by the FMA-pipe polynomial in attention2 / attention3 (0..3)
+// development: exponential pairs (of every 8) evaluated by the FMA-pipe polynomial in attention2_kernel (0..3)
 extern "C" int ur_debug_set_attention_poly(int n) {
   const int old = g_attn_poly;
   if (n >= 0 && n <= 3) g_attn_poly = n;
@@ -1592,7 +939,7 @@ extern "C" int ur_debug_set_attention_poly(int n) {
 // development: select the attention kernel generation (returns the previous one)
 extern "C" int ur_debug_set_attention_impl(int impl) {
   const int old = g_attn_impl;
-  if (impl >= 1 && impl <= 4) g_attn_impl = impl;
+  if (impl == 1 || impl == 2) g_attn_impl = impl;
   return old;
 }
 // development: device buffer of 64 int64 receiving clock64 timestamps (nullptr = off)
@@ -1634,23 +981,6 @@ extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void
   p.out_bs = out_bs;
   p.trace = g_attn_trace;
   if (head_dim == 512) return launch_attention512(p, mq, mk, mv, stream);
-  if (g_attn_impl == 4 && head_dim == 64) {
-    switch (g_attn_poly) {
-      case 0: return launch_attention4<0>(p, mq, mk, mv, stream);
-      case 1: return launch_attention4<1>(p, mq, mk, mv, stream);
-      case 2: return launch_attention4<2>(p, mq, mk, mv, stream);
-      default: return launch_attention4<3>(p, mq, mk, mv, stream);
-    }
-  }
-  if (g_attn_impl == 3) {
-    if (head_dim == 128) return launch_attention3<128, 1, kPolyOf8Default>(p, mq, mk, mv, stream);
-    switch (g_attn_poly) {
-      case 0: return launch_attention3<64, 2, 0>(p, mq, mk, mv, stream);
-      case 1: return launch_attention3<64, 2, 1>(p, mq, mk, mv, stream);
-      case 2: return launch_attention3<64, 2, 2>(p, mq, mk, mv, stream);
-      default: return launch_attention3<64, 2, 3>(p, mq, mk, mv, stream);
-    }
-  }
   if (g_attn_impl == 2) {
     if (head_dim == 128) return launch_attention2<128, 1, kPolyOf8Default>(p, mq, mk, mv, stream);
     switch (g_attn_poly) {
