@@ -8,6 +8,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from unirestore_b200 import ops  # noqa: E402
 
+NOFLUSH = "--noflush" in sys.argv
 dev = "cuda:0"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for (M, K, N, act, name) in [(32768, 320, 2560, ops.UR_ACT_GEGLU, "geglu64"), (8192, 640, 5120, ops.UR_ACT_GEGLU, "geglu32"),
@@ -23,7 +24,8 @@ for (M, K, N, act, name) in [(32768, 320, 2560, ops.UR_ACT_GEGLU, "geglu64"), (8
         ops.conv_gemm(x, w, N, bias=b, act=act, bn=bn)
     ts = []
     for _ in range(10):
-        flush.zero_()
+        if not NOFLUSH:
+            flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         ops.conv_gemm(x, w, N, bias=b, act=act, bn=bn)

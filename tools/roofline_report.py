@@ -80,7 +80,10 @@ def conv_family(x, w, n, kw):
         fam = "1x1 conv / linear, K<=640"
     else:
         fam = "1x1 conv / linear, K>640"
-    return fam, flops, byts
+    detail = "M=%d K=%d N=%d taps=%d act=%d%s%s%s" % (B * ho * wo, kper, n, taps, act, " +res" if kw.get("residual") is not None else "",
+                                                   " +stats" if kw.get("want_stats") or kw.get("stats") is not None else "",
+                                                   " x2" if c2 else "")
+    return fam, flops, byts, detail
 
 
 def wrap(name, key, cost):
@@ -139,6 +142,7 @@ KEYS = [("conv_gemm", "conv_gemm"), ("attention", "attention"), ("norm_apply", "
         ("dwconv3x3_gate", "dwconv3x3_gate"), ("scale_channels", "scale_channels")]
 idx = collections.Counter()
 rec = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])      # family -> [launches, flops, bytes, seconds]
+shapes = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])   # conv_gemm shape signature -> the same
 unmatched = 0
 for ev in evs:
     name = ev.name
@@ -149,7 +153,13 @@ for ev in evs:
             k = idx[key]
             idx[key] += 1
             if k < len(calls[key]):
-                fam, fl, by = calls[key][k]
+                fam, fl, by = calls[key][k][:3]
+                if len(calls[key][k]) > 3:
+                    S = shapes[calls[key][k][3]]
+                    S[0] += 1
+                    S[1] += fl
+                    S[2] += by
+                    S[3] += dur
             else:
                 unmatched += 1
             break
@@ -186,3 +196,10 @@ for t, fam, n, fl, by in rows:
     print("| %s | %d | %.2f | %.1f %% | %.1f | %.0f | %.0f | %.0f | %.0f | %.2f | %.2f | %s | %.2f |"
           % (fam, n, t * 1e3, 100 * t / tot_t, t / n * 1e6, fl / 1e9, by / 1e6, tf, gb, ft, fh,
              "tensor" if ft >= fh else "hbm", max(ft, fh)))
+
+print("\n## GEMM / conv launches by shape (top 45 by time)\n")
+print("| shape | launches | time ms | avg us | TFLOP/s | GB/s | tensor frac | HBM frac |")
+print("|---|---:|---:|---:|---:|---:|---:|---:|")
+for sig, (n, fl, by, t) in sorted(shapes.items(), key=lambda kv: -kv[1][3])[:45]:
+    print("| %s | %d | %.2f | %.1f | %.0f | %.0f | %.2f | %.2f |" % (sig, n, t * 1e3, t / n * 1e6, fl / t / 1e12, by / t / 1e9,
+                                                                fl / t / 1e12 / PT, by / t / 1e9 / PH))
