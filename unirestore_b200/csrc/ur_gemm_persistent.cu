@@ -66,7 +66,11 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
 
 __device__ __forceinline__ void group_barrier(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-template <int BN, bool PAIR>
+// LEAN = true: the epilogue of the common case only -- bias / temb row vector, optional residual and fused statistics,
+// per-warp TMA stores, no activation / gate / channel scale / alpha, no split-K -- so that the instruction footprint of
+// the ~80 % of launches that need nothing else is a third of the general kernel's (the 14 warps run four different
+// roles through one instruction cache; r2 ncu: 25 % of the epilogue warps' issue stalls were stall_no_inst).
+template <int BN, bool PAIR, bool LEAN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap mapA1,
                             const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapW,
@@ -96,7 +100,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : -1;
   const int u_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int u_stride = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  const bool tracing = !LEAN && p.trace != nullptr && blockIdx.x == 0;     // (the lean kernel carries no probes)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&mapA1);
@@ -147,8 +151,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       }
       for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumAProd == warp) {
-          const int s = kiter % STAGES;
-          const uint32_t ph = (kiter / STAGES) & 1;
+          const int rq = fast_div(kiter, p.fd_ring);
+          const int s = kiter - rq * p.ring;
+          const uint32_t ph = rq & 1;
           const bool trk = tracing && lane == 0 && warp == 0 && it == 1 && kb >= 6 && kb < 6 + 3 * 16;
           if (trk) p.trace[192 + 4 * ((kb - 6) / 3)] = clock64();
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -162,8 +167,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           const CUtensorMap* mp = src1 ? &mapA1 : &mapA2;
           const int cc = src1 ? c : c - p.c1;
           if (elect_one_sync()) {
-            // one arming arrive per stage (rank 0 only in PAIR mode), covering A and W bytes of both CTAs
-            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[s], PAIR ? 2 * kStageBytes : kStageBytes);
+            // one arming arrive per stage (rank 0 only in PAIR mode), covering A and W bytes of both CTAs (resident
+            // weights: after the CTA's first tile only the activation bytes arrive)
+            if (!PAIR || rank == 0)
+              mbar_expect_tx(&full_bar[s], PAIR ? 2 * kStageBytes : ((p.w_resident && it > 0) ? kABytes : kStageBytes));
             if constexpr (PAIR)
               tma_load_4d_2sm(sa, mp, &full_bar[s], cc, xi, yi, tc.b0);
             else
@@ -193,10 +200,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         tap = kb0 / p.cblocks;
         cb = kb0 - tap * p.cblocks;
       }
+      if (p.w_resident && it > 0) break;           // the weight tile of this CTA is already in its ring slots
       for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumWProd == me) {
-          const int s = kiter % STAGES;
-          const uint32_t ph = (kiter / STAGES) & 1;
+          const int rq = fast_div(kiter, p.fd_ring);
+          const int s = kiter - rq * p.ring;
+          const uint32_t ph = rq & 1;
           const bool trk = tracing && lane == 0 && me == 0 && it == 1 && kb >= 6 && kb < 6 + 2 * 16;
           if (trk) p.trace[256 + 4 * ((kb - 6) / 2)] = clock64();
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -224,6 +233,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);   // descriptor low word of stage 0 (LBO = 1)
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SW128
       uint32_t stage = 0, phase = 0;
+      const uint32_t rs = static_cast<uint32_t>(p.ring);     // ring stages in use (resident weights shrink the ring)
       int it = 0;
       for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
         const int as = it & 1;
@@ -244,7 +254,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           if (trk) p.trace[128 + 4 * ((kb - 8) >> 1)] = clock64();
           const uint32_t s0 = stage, ph0 = phase;
           uint32_t s1 = s0 + 1, ph1 = ph0;
-          if (s1 == STAGES) {
+          if (s1 == rs) {
             s1 = 0;
             ph1 ^= 1;
           }
@@ -256,13 +266,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           // advance the ring past the k-blocks consumed here and pre-test the next two
           stage = s1;
           phase = ph1;
-          if (two && ++stage == STAGES) {
+          if (two && ++stage == rs) {
             stage = 0;
             phase ^= 1;
           }
           {
             uint32_t n1 = stage + 1, nph1 = phase;
-            if (n1 == STAGES) {
+            if (n1 == rs) {
               n1 = 0;
               nph1 ^= 1;
             }
@@ -295,22 +305,22 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     const int r = q * 32 + lane;                  // tile row = TMEM lane
     const int et = threadIdx.x - kEpiWarp0 * 32;  // 0..255
     const int gt = et & 127;                      // thread index inside the warp group
-    const bool gated = p.act == UR_ACT_GEGLU || p.act == UR_ACT_GATE;
+    const bool gated = !LEAN && (p.act == UR_ACT_GEGLU || p.act == UR_ACT_GATE);
     const int n_out = gated ? (p.N >> 1) : p.N;
     const int ncols = gated ? (BN >> 1) : BN;
-    const bool has_mul = p.chscale != nullptr;
-    const bool plain = !gated && p.act == UR_ACT_NONE && !has_mul && p.alpha == 1.0f;
+    const bool has_mul = !LEAN && p.chscale != nullptr;
+    const bool plain = LEAN || (!gated && p.act == UR_ACT_NONE && !has_mul && p.alpha == 1.0f);
     // cooperative phase: thread gt moves 16-byte chunk (gt & 3) of rows (gt >> 2) + 32 i, i = 0..3
     const int cchunk = gt & 3;
     const int crow0 = gt >> 2;
     uint8_t* const stg_base = staging + grp * kEpiStageBytes;
     int sbuf = 0;                                 // staging buffer of the next sub-block (alternates)
-    const bool use_tma = p.tma_store != 0;
+    const bool use_tma = LEAN || p.tma_store != 0;
     // tma_store == 2 ("warp mode"): the output tensor map has a 32-row box and every epilogue WARP stores its own 32
     // rows (= its TMEM lane quarter) as soon as it has written them: no barrier between the four warps of a group on
     // the store path (the two 128-thread barriers per 32-column sub-block cost ~300 of its ~1 200 cycles, and the K <= 640
     // linears / GEGLU layers are epilogue-bound).  The residual is then staged by the warp for its own rows, too.
-    const bool warp_mode = p.tma_store == 2;
+    const bool warp_mode = LEAN || p.tma_store == 2;
     const int wrow0 = q * 32;                     // first tile row of this warp
     const int mrow0 = warp_mode ? wrow0 + (lane >> 2) : crow0;       // rows this thread moves: mrow0 + mstep * i
     const int mstep = warp_mode ? 8 : 32;
@@ -318,8 +328,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     // this thread's two columns (gt, gt + 128) of the NEXT tile's add / mul vectors (every warp group stages its own copy)
     float a_nx[2] = {0.f, 0.f}, m_nx[2] = {1.f, 1.f};
-    auto fetch_vec = [&](int tt) {
-      const TileCoord tn = tile_coord(p, fast_div(tt, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
+    auto fetch_vec = [&](const TileCoord& tn) {
       const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
       const int bb = tn.b0 < p.B ? tn.b0 : p.B - 1;      // (a PAIR ghost tile lies past the last image)
 #pragma unroll
@@ -335,13 +344,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         m_nx[h] = (has_mul && col < ncols && no0 + col < n_out) ? __ldg(p.chscale + bb * p.chscale_sb + no0 + col) : 1.f;
       }
     };
-    if (u_first < total_tiles) fetch_vec(u_first);
+    // (the coordinates of the next tile are computed once, for its vector fetch, and carried into the next iteration:
+    //  the epilogue is bound by its instruction count, r2 profiles/epilogue_store_experiments_r2.txt)
+    TileCoord tc = tile_coord(p, fast_div(u_first < total_tiles ? u_first : 0, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
+    TileCoord tn = tc;
+    if (u_first < total_tiles) fetch_vec(tc);
     int it = 0;
-    for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
-      const TileCoord tc = tile_coord(p, fast_div(t, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
+    for (int t = u_first; t < total_tiles; t += u_stride, ++it, tc = tn) {
+      const bool has_next = t + u_stride < total_tiles;
+      if (has_next) tn = tile_coord(p, fast_div(t + u_stride, p.fd_ksplit), n_tiles, BN, Wt, Ht, Bt, rank);
       const int nout0 = gated ? (tc.n0 >> 1) : tc.n0;
       const int as = it & 1;
-      if (p.ws) {
+      if (!LEAN && p.ws) {
         // ---- split-K: this unit's fp32 partial tile goes to slab `ks` of the workspace with plain 16-byte stores
         //      (every element of every slab is written exactly once: no zero fill, no atomics, and the sum order in
         //      splitk_finish_kernel is fixed -> bit-reproducible); bias / residual / bf16 conversion / GroupNorm
@@ -380,14 +394,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       for (int h = 0; h < 2; ++h) {
         if (gt + 128 * h < BN) {
           add[gt + 128 * h] = a_nx[h];
-          mul[gt + 128 * h] = m_nx[h];
+          if (!LEAN) mul[gt + 128 * h] = m_nx[h];
         }
       }
-      if (t + u_stride < total_tiles) fetch_vec(t + u_stride);
+      if (has_next) fetch_vec(tn);
       // global element offsets of the 4 rows this thread moves in the cooperative phases (-1: outside the tensor)
-      long long roff[4];
+      long long roff[4] = {-1, -1, -1, -1};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
+        if (!p.residual && (use_tma || LEAN)) break;        // only the residual fetch and the st.global path use them
         const int rr = mrow0 + mstep * i;
         const int x = tc.x0 + (rr & (Wt - 1)), y = tc.y0 + ((rr >> p.wt_log2) & (Ht - 1));
         const int b = tc.b0 + (rr >> (p.wt_log2 + p.ht_log2));
@@ -442,7 +457,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(stg + stg_off(mrow0 + mstep * i, mchunk)) = rres[i];
           if (warp_mode) __syncwarp(); else group_barrier(4 + grp);
-          // prefetch the residual of this group's next sub-block
+          // prefetch the residual of this group's next sub-block (the proxy fence below = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC
+          // waits for these loads if they are still in flight; r2 ablation: most of the +5.6 us a residual costs on the
+          // 64x64-level linears is its 21 MB of traffic, ~2 us is exposed latency)
           const int cn = c + 64;
           const int col = cn + mchunk * 8;
           const bool okc = cn < ncols && nout0 + col + 8 <= n_out;
@@ -732,20 +749,21 @@ int launch_splitk_finish(const GemmParams& p, cudaStream_t stream) {
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "splitk_finish launch");
 }
 
-template <int BN, bool PAIR>
+template <int BN, bool PAIR, bool LEAN>
 static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                    const CUtensorMap& mo, int total_units, int n_tiles, cudaStream_t stream) {
+                    const CUtensorMap& mo, int total_units, int n_tiles, cudaStream_t stream, int max_ctas) {
   using Cfg = PCfg<BN, PAIR>;
   constexpr int smem = Cfg::kSmem;
   static_assert(smem <= 227 * 1024 && Cfg::kStages >= 3, "shared memory budget");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, PAIR>,
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_persistent_kernel<BN, PAIR, LEAN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm_persistent)");
     configured = true;
   }
-  const int slots = PAIR ? num_sms() / 2 : num_sms();
+  int slots = PAIR ? num_sms() / 2 : num_sms();
+  if (max_ctas > 0 && !PAIR && max_ctas < slots) slots = max_ctas;
   const int units = total_units < slots ? total_units : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(PAIR ? 2 * units : units);
@@ -761,26 +779,45 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_persistent_kernel<BN, PAIR>, p, a1, a2, w, mo, total_units, n_tiles);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_persistent_kernel<BN, PAIR, LEAN>, p, a1, a2, w, mo, total_units, n_tiles);
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "conv_gemm_persistent launch");
+}
+
+static int g_lean_epilogue = getenv("UR_GEMM_LEAN") ? atoi(getenv("UR_GEMM_LEAN")) : 1;   // development: 0 = general kernel always
+
+int persistent_stages(int bn, bool pair) {
+  if (pair)
+    return bn == 64 ? PCfg<64, true>::kStages : bn == 128 ? PCfg<128, true>::kStages
+         : bn == 160 ? PCfg<160, true>::kStages : PCfg<256, true>::kStages;
+  return bn == 64 ? PCfg<64, false>::kStages : bn == 128 ? PCfg<128, false>::kStages
+       : bn == 160 ? PCfg<160, false>::kStages : PCfg<256, false>::kStages;
 }
 
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
                                 const CUtensorMap& mo, bool pair, int bn, int total_units, int n_tiles,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, int max_ctas) {
+  const bool lean = g_lean_epilogue && p.act == UR_ACT_NONE && !p.chscale && p.alpha == 1.0f && p.tma_store == 2 && !p.ws;
   if (pair) {
     switch (bn) {
-      case 64: return launch_p<64, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
-      case 128: return launch_p<128, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
-      case 160: return launch_p<160, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
-      default: return launch_p<256, true>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      case 64: return lean ? launch_p<64, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<64, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+      case 128: return lean ? launch_p<128, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<128, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+      case 160: return lean ? launch_p<160, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<160, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+      default: return lean ? launch_p<256, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<256, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
     }
   }
   switch (bn) {
-    case 64: return launch_p<64, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
-    case 128: return launch_p<128, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
-    case 160: return launch_p<160, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
-    default: return launch_p<256, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    case 64: return lean ? launch_p<64, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<64, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+    case 128: return lean ? launch_p<128, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<128, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+    case 160: return lean ? launch_p<160, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<160, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+    default: return lean ? launch_p<256, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
+                  : launch_p<256, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
   }
 }
 
