@@ -239,13 +239,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int b_mn_ma
 
 // ------------------------------------------------------------------ math
 // x * sigmoid(x) with MUFU ex2 + MUFU rcp (relative error ~1e-6, far below the bf16 rounding of the result)
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// (raw MUFU.RCP: __fdividef wraps the same instruction in a range guard for |denominator| > 2^126 -- five more issue
+//  slots per element -- that the denominators here, 1 + e^-x and 1 + 0.33 |x|, cannot need: for them rcp(inf) = 0 is the
+//  right limit)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.0f + __expf(-x)); }
 // exact-erf GELU (nn.GELU() default, GEGLU).  erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16
 // rounding of the result): branch-free, 2 MUFU (ex2, rcp) + ~12 FP32 ops instead of the ~40-instruction branchy erff
 // (the GEGLU epilogue evaluates 16 384 of these per 128x256 accumulator tile and was bound by it).
 __device__ __forceinline__ float erf_as_f(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
@@ -287,7 +295,7 @@ __device__ __forceinline__ f2 gelu_erf2(f2 x) {
   const f2 xs = mul2(x, splat2(0.70710678118654752f));
   const f2 ax = f2{fabsf(xs.x), fabsf(xs.y)};
   const f2 den = fma2(ax, splat2(0.3275911f), splat2(1.0f));
-  const f2 t = f2{__fdividef(1.0f, den.x), __fdividef(1.0f, den.y)};
+  const f2 t = f2{rcp_approx(den.x), rcp_approx(den.y)};
   f2 pl = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
   pl = fma2(pl, t, splat2(1.421413741f));
   pl = fma2(pl, t, splat2(-0.284496736f));
