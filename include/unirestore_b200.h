@@ -112,9 +112,6 @@ int ur_debug_set_gemm_splitk(int on);
  * barrier), 2 = one TMA store per epilogue warp (32-row boxes, no barrier on the store path; default); returns the
  * previous value. */
 int ur_debug_set_gemm_tma_store(int on);
-/* Development: 0 = small-K layers stream their weight tile for every M tile instead of keeping it resident in the
- * shared-memory ring (persistent kernel); returns the previous value. */
-int ur_debug_set_gemm_w_resident(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 /* Development: attention kernel generation for head_dim 64 / 128: 1 = attention_kernel (default: two softmax threads per
  * row, two CTAs per SM), 2 = attention2_kernel (two query tiles per CTA, one softmax thread per row, single TMEM pass, P in

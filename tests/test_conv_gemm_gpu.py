@@ -318,36 +318,3 @@ def test_epilogue_store_modes_agree(B, H, W, Cin, Cout, taps):
         assert torch.equal(outs[mode][0], outs[2][0]), "store mode %d output differs from warp mode" % mode
         scale = outs[2][1].abs().amax().clamp_min(1e-6)
         assert ((outs[mode][1] - outs[2][1]).abs() / scale).max().item() < 1e-6
-
-
-@pytest.mark.parametrize("B,H,W,Cin,Cout,taps", [(8, 64, 64, 320, 320, 1), (4, 128, 128, 192, 128, 1), (3, 100, 70, 320, 960, 1),
-                                                 (2, 128, 128, 64, 64, 3), (8, 64, 64, 256, 200, 1), (16, 1, 4096, 320, 640, 1),
-                                                 (4, 128, 128, 128, 128, 1)])
-def test_resident_weights_agree(B, H, W, Cin, Cout, taps):
-    """Small-K layers keep their weight tile in the shared-memory ring for all M tiles of a CTA (ring shrunk to the
-    k-block count -- 3, 4 or 5 slots here --, CTA count a multiple of the N tile count): outputs and fused statistics are
-    bit-identical to the streamed-weights schedule, and right against torch, on full and ragged tiles.  (K = 128: two
-    k-blocks, fewer than the three activation-producer warps -> stays on the streamed schedule.)"""
-    from unirestore_b200 import _cabi, ops
-    x = _rand(B, Cin, H, W, seed=140)
-    tp = {1: ops.TAPS_1x1, 9: ops.TAPS_3x3, 3: ((0, -1), (0, 0), (0, 1))}[taps]
-    kh, kw = (3, 3) if taps == 9 else ((1, 3) if taps == 3 else (1, 1))
-    w = _rand(Cout, Cin, kh, kw, seed=141, scale=(taps * Cin) ** -0.5)
-    b = _rand(Cout, seed=142)
-    r = _rand(B, H, W, Cout, seed=143).to(torch.bfloat16)
-    xb, wp = _nhwc(x), ops.pack_conv_weight(w.to(torch.bfloat16))
-    outs = {}
-    for mode in (1, 0):
-        old = _cabi.lib().ur_debug_set_gemm_w_resident(mode)
-        try:
-            y = ops.conv_gemm(xb, wp, Cout, taps=tp, bias=b, residual=r, want_stats=True)
-            torch.cuda.synchronize()
-            outs[mode] = (y.clone(), y._ur_stats.clone())
-        finally:
-            _cabi.lib().ur_debug_set_gemm_w_resident(old)
-    ref = bf16_round(F.conv2d(xb.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), b, padding=(kh // 2, kw // 2))
-                     .permute(0, 2, 3, 1) + r.float())
-    assert_close(outs[1][0], ref, TOL, "resident weights %s" % ((B, H, W, Cin, Cout, taps),))
-    assert torch.equal(outs[0][0], outs[1][0]), "resident-weights output differs from the streamed schedule"
-    scale = outs[1][1].abs().amax().clamp_min(1e-6)
-    assert ((outs[0][1] - outs[1][1]).abs() / scale).max().item() < 1e-6

@@ -56,7 +56,6 @@ SIGNATURES = {
     "ur_debug_set_gemm_pair_mode": (C.c_int, [C.c_int]),
     "ur_debug_set_gemm_splitk": (C.c_int, [C.c_int]),
     "ur_debug_set_gemm_tma_store": (C.c_int, [C.c_int]),
-    "ur_debug_set_gemm_w_resident": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_trace": (C.c_int, [_P]),
     "ur_debug_set_attention_impl": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_poly": (C.c_int, [C.c_int]),

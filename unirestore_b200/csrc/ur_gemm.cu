@@ -305,12 +305,6 @@ extern "C" int ur_debug_set_gemm_tma_store(int on) {
   g_tma_store = on;
   return old;
 }
-static int g_w_resident = getenv("UR_GEMM_WRES") ? atoi(getenv("UR_GEMM_WRES")) : 1;   // 0: weights are always streamed
-extern "C" int ur_debug_set_gemm_w_resident(int on) {
-  const int old = g_w_resident;
-  g_w_resident = on;
-  return old;
-}
 static int g_split_mode = getenv("UR_GEMM_SPLITK") ? atoi(getenv("UR_GEMM_SPLITK")) : 1;   // 0: never split K
 extern "C" int ur_debug_set_gemm_splitk(int on) {
   const int old = g_split_mode;
@@ -565,9 +559,6 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
     const long long total = static_cast<long long>(n_tiles) * (pair_path ? (m_tiles + 1) / 2 : m_tiles);
     if (total > 0x3fffffffLL) return set_error(UR_ERR_ARG, "ur_conv_gemm: too many tiles");
     p.ksplit = 1;
-    p.ring = persistent_stages(bn, pair_path);
-    p.fd_ring = make_fastdiv(static_cast<uint32_t>(p.ring));
-    p.w_resident = 0;
     p.fd_ntiles = make_fastdiv(static_cast<uint32_t>(n_tiles));
     p.fd_ksplit = make_fastdiv(1);
     p.fd_tx = make_fastdiv(static_cast<uint32_t>(p.tiles_x));
@@ -595,22 +586,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
         return launch_splitk_finish(p, stream);
       }
     }
-    // Resident weights (round 2).  The small-K linears are bound by the operand stream L2 -> shared memory, not by the
-    // tensor core or the epilogue (profiles/epilogue_store_experiments_r2.txt): a 128 x 160 tile with K = 320 pulls 80 KB
-    // of activations and 100 KB of weights for 13 MFLOP, and the weights are the same for every M tile.  When the whole
-    // K extent fits the ring (k-blocks per tile <= compiled stages) the ring is shrunk to exactly that many slots, so
-    // slot kb always holds k-block kb; with a CTA count that is a multiple of the N tile count every CTA keeps ONE N
-    // tile for all its M tiles and loads its weights once.  (>= 3 slots: with fewer slots than activation-producer
-    // warps a producer could run two barrier phases ahead of the consumer, which a parity wait cannot tell apart.)
-    int max_ctas = 0;
-    if (g_w_resident && !pair_path && !d->w_batched && n_tiles <= num_sms() / 2 && nkb_total >= 3 &&
-        nkb_total <= persistent_stages(bn, false) && total >= 2LL * num_sms()) {
-      p.ring = nkb_total;
-      p.w_resident = 1;
-      max_ctas = (num_sms() / n_tiles) * n_tiles;
-    }
-    p.fd_ring = make_fastdiv(static_cast<uint32_t>(p.ring));
-    int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total), n_tiles, stream, max_ctas);
+    int rc = launch_conv_gemm_persistent(p, mA1, mA2, mW, mO, pair_path, bn, static_cast<int>(total), n_tiles, stream);
     if (rc || !d->stats || stats_fused) return rc;
     return stats_fallback(d, n_out, stream);
   }

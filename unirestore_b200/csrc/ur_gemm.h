@@ -61,11 +61,6 @@ struct GemmParams {
   int ksplit;         // split-K factor (1 = off); work unit u -> (tile u / ksplit, K slice u % ksplit)
   float* ws;          // split-K: fp32 [ksplit][B*Ho*Wo, N] partial-sum slabs (plain stores), epilogue deferred to splitk_finish
   long long ws_slab;  // elements per slab = B*Ho*Wo*N
-  int ring;           // persistent kernel: shared-memory ring stages in use (<= compiled stages; = k-blocks per tile when
-                      //   w_resident, so that ring slot kb always holds k-block kb)
-  FastDiv fd_ring;
-  int w_resident;     // persistent kernel: every tile of a CTA has the same N tile and the whole K extent of its weight tile
-                      //   fits the ring: the weights are loaded for the CTA's first tile only and stay in shared memory
   long long* trace;   // development: per-role clock64 timestamps of CTA 0 (nullptr = off)
 };
 
@@ -79,8 +74,6 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 int launch_splitk_finish(const GemmParams& p, cudaStream_t stream);
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
                                 const CUtensorMap& mo, bool pair, int bn, int total_units, int n_tiles,
-                                cudaStream_t stream, int max_ctas = 0);
-// shared-memory ring stages the persistent kernel is compiled with for this tile configuration
-int persistent_stages(int bn, bool pair);
+                                cudaStream_t stream);
 
 }  // namespace ur

@@ -151,9 +151,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       }
       for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumAProd == warp) {
-          const int rq = fast_div(kiter, p.fd_ring);
-          const int s = kiter - rq * p.ring;
-          const uint32_t ph = rq & 1;
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
           const bool trk = tracing && lane == 0 && warp == 0 && it == 1 && kb >= 6 && kb < 6 + 3 * 16;
           if (trk) p.trace[192 + 4 * ((kb - 6) / 3)] = clock64();
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -167,10 +166,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           const CUtensorMap* mp = src1 ? &mapA1 : &mapA2;
           const int cc = src1 ? c : c - p.c1;
           if (elect_one_sync()) {
-            // one arming arrive per stage (rank 0 only in PAIR mode), covering A and W bytes of both CTAs (resident
-            // weights: after the CTA's first tile only the activation bytes arrive)
-            if (!PAIR || rank == 0)
-              mbar_expect_tx(&full_bar[s], PAIR ? 2 * kStageBytes : ((p.w_resident && it > 0) ? kABytes : kStageBytes));
+            // one arming arrive per stage (rank 0 only in PAIR mode), covering A and W bytes of both CTAs
+            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[s], PAIR ? 2 * kStageBytes : kStageBytes);
             if constexpr (PAIR)
               tma_load_4d_2sm(sa, mp, &full_bar[s], cc, xi, yi, tc.b0);
             else
@@ -200,12 +197,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         tap = kb0 / p.cblocks;
         cb = kb0 - tap * p.cblocks;
       }
-      if (p.w_resident && it > 0) break;           // the weight tile of this CTA is already in its ring slots
       for (int kb = kb0; kb < kb1; ++kb, ++kiter) {
         if (kiter % kNumWProd == me) {
-          const int rq = fast_div(kiter, p.fd_ring);
-          const int s = kiter - rq * p.ring;
-          const uint32_t ph = rq & 1;
+          const int s = kiter % STAGES;
+          const uint32_t ph = (kiter / STAGES) & 1;
           const bool trk = tracing && lane == 0 && me == 0 && it == 1 && kb >= 6 && kb < 6 + 2 * 16;
           if (trk) p.trace[256 + 4 * ((kb - 6) / 2)] = clock64();
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -233,7 +228,6 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);   // descriptor low word of stage 0 (LBO = 1)
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);       // SBO 1024 B, version 1, SW128
       uint32_t stage = 0, phase = 0;
-      const uint32_t rs = static_cast<uint32_t>(p.ring);     // ring stages in use (resident weights shrink the ring)
       int it = 0;
       for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
         const int as = it & 1;
@@ -254,7 +248,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           if (trk) p.trace[128 + 4 * ((kb - 8) >> 1)] = clock64();
           const uint32_t s0 = stage, ph0 = phase;
           uint32_t s1 = s0 + 1, ph1 = ph0;
-          if (s1 == rs) {
+          if (s1 == STAGES) {
             s1 = 0;
             ph1 ^= 1;
           }
@@ -266,13 +260,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
           // advance the ring past the k-blocks consumed here and pre-test the next two
           stage = s1;
           phase = ph1;
-          if (two && ++stage == rs) {
+          if (two && ++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
           {
             uint32_t n1 = stage + 1, nph1 = phase;
-            if (n1 == rs) {
+            if (n1 == STAGES) {
               n1 = 0;
               nph1 ^= 1;
             }
@@ -751,7 +745,7 @@ int launch_splitk_finish(const GemmParams& p, cudaStream_t stream) {
 
 template <int BN, bool PAIR, bool LEAN>
 static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
-                    const CUtensorMap& mo, int total_units, int n_tiles, cudaStream_t stream, int max_ctas) {
+                    const CUtensorMap& mo, int total_units, int n_tiles, cudaStream_t stream) {
   using Cfg = PCfg<BN, PAIR>;
   constexpr int smem = Cfg::kSmem;
   static_assert(smem <= 227 * 1024 && Cfg::kStages >= 3, "shared memory budget");
@@ -762,8 +756,7 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_gemm_persistent)");
     configured = true;
   }
-  int slots = PAIR ? num_sms() / 2 : num_sms();
-  if (max_ctas > 0 && !PAIR && max_ctas < slots) slots = max_ctas;
+  const int slots = PAIR ? num_sms() / 2 : num_sms();
   const int units = total_units < slots ? total_units : slots;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(PAIR ? 2 * units : units);
@@ -785,39 +778,31 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
 
 static int g_lean_epilogue = getenv("UR_GEMM_LEAN") ? atoi(getenv("UR_GEMM_LEAN")) : 1;   // development: 0 = general kernel always
 
-int persistent_stages(int bn, bool pair) {
-  if (pair)
-    return bn == 64 ? PCfg<64, true>::kStages : bn == 128 ? PCfg<128, true>::kStages
-         : bn == 160 ? PCfg<160, true>::kStages : PCfg<256, true>::kStages;
-  return bn == 64 ? PCfg<64, false>::kStages : bn == 128 ? PCfg<128, false>::kStages
-       : bn == 160 ? PCfg<160, false>::kStages : PCfg<256, false>::kStages;
-}
-
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
                                 const CUtensorMap& mo, bool pair, int bn, int total_units, int n_tiles,
-                                cudaStream_t stream, int max_ctas) {
+                                cudaStream_t stream) {
   const bool lean = g_lean_epilogue && p.act == UR_ACT_NONE && !p.chscale && p.alpha == 1.0f && p.tma_store == 2 && !p.ws;
   if (pair) {
     switch (bn) {
-      case 64: return lean ? launch_p<64, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<64, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
-      case 128: return lean ? launch_p<128, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<128, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
-      case 160: return lean ? launch_p<160, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<160, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
-      default: return lean ? launch_p<256, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<256, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+      case 64: return lean ? launch_p<64, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<64, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      case 128: return lean ? launch_p<128, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<128, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      case 160: return lean ? launch_p<160, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<160, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+      default: return lean ? launch_p<256, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<256, true, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
     }
   }
   switch (bn) {
-    case 64: return lean ? launch_p<64, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<64, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
-    case 128: return lean ? launch_p<128, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<128, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
-    case 160: return lean ? launch_p<160, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<160, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
-    default: return lean ? launch_p<256, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas)
-                  : launch_p<256, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream, max_ctas);
+    case 64: return lean ? launch_p<64, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<64, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    case 128: return lean ? launch_p<128, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<128, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    case 160: return lean ? launch_p<160, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<160, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
+    default: return lean ? launch_p<256, false, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
+                  : launch_p<256, false, false>(p, a1, a2, w, mo, total_units, n_tiles, stream);
   }
 }
 
