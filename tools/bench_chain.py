@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ring", default="1,2,6")
 ap.add_argument("--reps", type=int, default=48)
 ap.add_argument("--cases", default="")
+ap.add_argument("--gbn", type=int, default=0, help="force the N tile of the gated cases (0 = library choice)")
+ap.add_argument("--bn", type=int, default=0, help="force the N tile of the non-gated cases (0 = library choice)")
 a = ap.parse_args()
 dev = "cuda:0"
 CASES = [(32768, 320, 320, ops.UR_ACT_NONE, False, False, "lin64"), (32768, 320, 320, ops.UR_ACT_NONE, True, False, "lin64+res"),
@@ -24,7 +26,9 @@ CASES = [(32768, 320, 320, ops.UR_ACT_NONE, False, False, "lin64"), (32768, 320,
          (32768, 320, 320, ops.UR_ACT_GELU, False, False, "gelu64"), (32768, 320, 2560, ops.UR_ACT_GEGLU, False, False, "geglu64"),
          (8192, 640, 5120, ops.UR_ACT_GEGLU, False, False, "geglu32"), (32768, 1280, 320, ops.UR_ACT_NONE, True, False, "ffout64+res"),
          (8192, 640, 640, ops.UR_ACT_NONE, True, False, "lin32+res"), (8192, 640, 1920, ops.UR_ACT_NONE, False, False, "qkv32"),
-         (2048, 1280, 1280, ops.UR_ACT_NONE, True, False, "lin16+res")]
+         (2048, 1280, 1280, ops.UR_ACT_NONE, True, False, "lin16+res"), (2048, 1280, 10240, ops.UR_ACT_GEGLU, False, False, "geglu16"),
+         (32768, 320, 2560, ops.UR_ACT_NONE, False, False, "wide64"), (2048, 1280, 3840, ops.UR_ACT_NONE, False, False, "qkv16"),
+         (32768, 256, 768, ops.UR_ACT_NONE, False, False, "naf768")]
 if a.cases:
     CASES = [c for c in CASES if c[-1] in a.cases.split(",")]
 for (M, K, N, act, res, stats, name) in CASES:
@@ -33,7 +37,7 @@ for (M, K, N, act, res, stats, name) in CASES:
         xs = [torch.randn(8, M // 8, K, device=dev).to(torch.bfloat16) for _ in range(ring)]
         w = (torch.randn(N, K, device=dev) * K ** -0.5).to(torch.bfloat16)
         b = torch.randn(N, device=dev)
-        bn = ops.pick_bn(N, True) if act == ops.UR_ACT_GEGLU else 0
+        bn = (a.gbn or ops.pick_bn(N, True)) if act == ops.UR_ACT_GEGLU else a.bn
         if act == ops.UR_ACT_GEGLU:
             w, b = ops.pack_gated_weight(w, b, bn)
         n_out = N // 2 if act == ops.UR_ACT_GEGLU else N

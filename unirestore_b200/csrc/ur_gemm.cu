@@ -318,8 +318,8 @@ extern "C" int ur_debug_set_gemm_pair_mode(int mode) {
   return old;
 }
 
-static void pick_tile_config(int n, long long m_tiles, int nkb, int fixed_bn, bool pair_legal, int* bn_out,
-                             bool* pair_out) {
+static void pick_tile_config(int n, long long m_tiles, int nkb, int fixed_bn, bool pair_legal, bool short_k_linear,
+                             int* bn_out, bool* pair_out) {
   const int cands[4] = {256, 160, 128, 64};
   const int sms = num_sms();
   double best_cost = -1.0;
@@ -328,6 +328,11 @@ static void pick_tile_config(int n, long long m_tiles, int nkb, int fixed_bn, bo
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     if (fixed_bn && bn != fixed_bn) continue;
+    // Round 2 (tools/bench_chain.py, profiles/epilogue_store_experiments_r2.txt): short-K linears whose N is a multiple of
+    // 160 run faster on 160-wide tiles than the rounds x k-block-time model predicts for 256 (QKV projections N = 960 /
+    // 1920 / 3840: 27.5 vs 30.0, 22.9 vs 28.3, 17.9 vs 18.6 us) -- a 256-wide stage is 48 KB, only three fit, and with
+    // 5..20 k-blocks per tile the ring never reaches a steady state
+    if (!fixed_bn && short_k_linear && n % 160 == 0 && bn != 160) continue;
     const long long n_tiles = (n + bn - 1) / bn;
     for (int pair = 0; pair < 2; ++pair) {
       if (pair && (!pair_legal || g_pair_mode == 0)) continue;
@@ -415,7 +420,7 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
   int bn = 0;
   bool pair = false;
   pick_tile_config(d->n, best_cost, d->ntaps * (((d->group_kc ? d->group_kc : ctot) + 63) / 64), d->bn ? d->bn : (gated ? ur_conv_gemm_pick_bn(d->n, 1) : 0),
-                   !d->w_batched && best_cost >= 2, &bn, &pair);
+                   !d->w_batched && best_cost >= 2, d->ntaps == 1 && !d->group_kc && (ctot + 63) / 64 <= 20, &bn, &pair);
   if (split_ok) {
     bn = d->n % 160 == 0 ? 160 : 128;
     pair = best_cost >= 2 && g_pair_mode != 0;
