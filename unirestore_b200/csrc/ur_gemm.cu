@@ -299,6 +299,7 @@ extern "C" int ur_conv_gemm_pick_bn(int n, int gated) {
 // shared-memory traffic of TMA write + UMMA read, (16 KB + W bytes) * 2 / 128 B per cycle, and ~75 cycles of issue
 // per tcgen05.mma.  A pair stages only bn/2 weight rows per CTA.
 // epilogue stores: 0 = st.global, 1 = one TMA store per 128-row sub-block (group barrier), 2 = one per warp (default)
+static int g_lean_epilogue = getenv("UR_GEMM_LEAN") ? atoi(getenv("UR_GEMM_LEAN")) : 1;   // development: 0 = general kernel always
 static int g_tma_store = getenv("UR_GEMM_TMA_STORE") ? atoi(getenv("UR_GEMM_TMA_STORE")) : 2;
 extern "C" int ur_debug_set_gemm_tma_store(int on) {
   const int old = g_tma_store;
@@ -542,14 +543,17 @@ extern "C" int ur_conv_gemm(const ur_conv_desc* d, void* stream_v) {
       // warp mode (tma_store = 2): a 32-row box = the rows of ONE epilogue warp (32 consecutive tile rows are 32 pixels of
       // a row, or 32 / Wt rows of Wt pixels, inside one image as long as an image contributes >= 32 rows to the tile);
       // otherwise one box per 128-row sub-block issued after a group barrier (tma_store = 1)
-      const bool warp_box = g_tma_store != 1 && Wt * Ht >= 32;
+      // the lean kernel (bias / residual / statistics only; ur_gemm_persistent.cu) stores through its store warps: 128-row
+      // boxes like mode 1, tma_store = 4
+      const bool lean = g_lean_epilogue && g_tma_store == 2 && d->act == UR_ACT_NONE && !d->chscale && d->alpha == 1.0f && !split_ok;
+      const bool warp_box = !lean && g_tma_store != 1 && Wt * Ht >= 32;
       const uint32_t bwx = static_cast<uint32_t>(Wt < 32 ? Wt : 32);
       const uint32_t box_g[4] = {32u, static_cast<uint32_t>(Wt), static_cast<uint32_t>(Ht), static_cast<uint32_t>(Bt)};
       const uint32_t box_w[4] = {32u, bwx, 32u / bwx, 1u};
       const uint32_t es[4] = {1u, 1u, 1u, 1u};
       const bool str_ok = d->out_sx > 0 && (d->hout == 1 || d->out_sy > 0) && (d->batch == 1 || d->out_sb > 0);
       if (str_ok && encode_tensor_map(&mO, d->out, 4, dims, str, warp_box ? box_w : box_g, es, 64) == UR_OK)
-        p.tma_store = warp_box ? 2 : 1;
+        p.tma_store = lean ? 4 : (warp_box ? 2 : 1);
     }
     // GroupNorm statistics of the output: fused into the epilogue when an M tile never spans two images and K is not
     // split; otherwise a ur_chan_stats pass over the finished output (dense pixel pitch required) does the same

@@ -57,7 +57,8 @@ struct GemmParams {
   int act;
   double* stats;      // persistent kernel: (sum, sumsq) of the bf16 output per (image, channel) accumulated here (GroupNorm
   int stats_ld;       //   statistics fused into the epilogue); channel n of image b at stats[(b * stats_ld + n) * 2]
-  int tma_store;      // persistent kernel: 0 = coalesced st.global, 1 = one TMA store per 128-row sub-block, 2 = one per warp
+  int tma_store;      // persistent kernel: 0 = coalesced st.global, 1 = one TMA store per 128-row sub-block, 2 = one per warp,
+                      //   4 = lean kernel: one per sub-block issued by the group's store warp
   int ksplit;         // split-K factor (1 = off); work unit u -> (tile u / ksplit, K slice u % ksplit)
   float* ws;          // split-K: fp32 [ksplit][B*Ho*Wo, N] partial-sum slabs (plain stores), epilogue deferred to splitk_finish
   long long ws_slab;  // elements per slab = B*Ho*Wo*N

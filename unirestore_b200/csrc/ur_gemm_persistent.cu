@@ -11,6 +11,9 @@
 //                 tcgen05.ld -> +bias/+temb (staged in smem) -> activation / GEGLU / gate -> channel scale
 //                 -> +residual -> bf16 -> padded smem tile -> coalesced 16-byte global stores (8 rows x 64 B per
 //                 warp instruction instead of 32 scattered rows)
+//     warps 14..15 (lean kernel) TMA-store issuers, one per epilogue warp group: issuing a 4-D tiled TMA store costs its
+//                 thread ~340 cycles, a third of a 32-column sub-block when lane 0 of an epilogue warp does it while the
+//                 other 31 lanes wait; the epilogue warps only fence + arrive on an mbarrier and go on
 //   smem ring of STAGES x (A 128x64 bf16 + W BNx64 bf16), 128-byte swizzle, full/empty mbarriers.
 //
 // Same arithmetic and operand layout as ur_gemm.cu (see there / include/unirestore_b200.h for the reference
@@ -27,7 +30,8 @@ __device__ __forceinline__ int stg_off(int row, int chunk) { return row * 64 + (
 constexpr int kNumAProd = 3, kNumWProd = 2;
 constexpr int kMmaWarp = kNumAProd + kNumWProd;      // 5
 constexpr int kEpiWarp0 = kMmaWarp + 1;              // 6
-constexpr int kThreads = (kEpiWarp0 + 8) * 32;       // 448
+constexpr int kStoreWarp0 = kEpiWarp0 + 8;           // 14: one TMA-store issuer per epilogue warp group (lean kernel)
+constexpr int kThreads = (kStoreWarp0 + 2) * 32;     // 512
 
 // PAIR = true: CTA pairs (cluster of 2) run tcgen05.mma.cta_group::2 on a 256 x BN tile; each CTA stages its own
 // 128 activation rows and HALF of the weight rows, which halves the weight traffic into shared memory (the main
@@ -88,7 +92,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* store_req = tempty_bar + 2;       // [2 groups][2 staging buffers]: the group's 4 warps have staged a sub-block
+  uint64_t* store_done = store_req + 4;       // [2][2]: the TMA store issued from the buffer has finished reading it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(store_done + 4);
 
   const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5));
   const int lane = threadIdx.x & 31;
@@ -114,6 +120,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], PAIR ? 512 : 256);      // PAIR: the peer's epilogue threads arrive remotely on rank 0
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&store_req[s], 4);
+      mbar_init(&store_done[s], 1);
     }
     fence_barrier_init();
   }
@@ -292,7 +302,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         if (tracing && lane == 0 && it < 8) p.trace[3 * 16 + it] = clock64();
       }
     }
-  } else {
+  } else if (warp < kStoreWarp0) {
     // =============================== epilogue ===============================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int grp = (warp - kEpiWarp0) >> 2;      // warp group 0 / 1
@@ -310,15 +320,20 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     uint8_t* const stg_base = staging + grp * kEpiStageBytes;
     int sbuf = 0;                                 // staging buffer of the next sub-block (alternates)
     const bool use_tma = LEAN || p.tma_store != 0;
+    // lean kernel: "store-warp mode" -- the four warps of a group stage their rows, fence, arrive on store_req, and warp
+    // 14 + grp issues ONE TMA store per sub-block (128-row box) and reports on store_done when the buffer is free again
+    constexpr bool sw_mode = LEAN;
+    uint32_t nsub = 0;                            // sub-blocks this group has staged so far (buffer nsub & 1)
     // tma_store == 2 ("warp mode"): the output tensor map has a 32-row box and every epilogue WARP stores its own 32
     // rows (= its TMEM lane quarter) as soon as it has written them: no barrier between the four warps of a group on
     // the store path (the two 128-thread barriers per 32-column sub-block cost ~300 of its ~1 200 cycles, and the K <= 640
     // linears / GEGLU layers are epilogue-bound).  The residual is then staged by the warp for its own rows, too.
-    const bool warp_mode = LEAN || p.tma_store == 2;
+    const bool warp_mode = !LEAN && p.tma_store == 2;
+    const bool warp_rows = LEAN || warp_mode;     // every warp moves / stages only its own 32 rows (no group barriers)
     const int wrow0 = q * 32;                     // first tile row of this warp
-    const int mrow0 = warp_mode ? wrow0 + (lane >> 2) : crow0;       // rows this thread moves: mrow0 + mstep * i
-    const int mstep = warp_mode ? 8 : 32;
-    const int mchunk = warp_mode ? (lane & 3) : cchunk;
+    const int mrow0 = warp_rows ? wrow0 + (lane >> 2) : crow0;       // rows this thread moves: mrow0 + mstep * i
+    const int mstep = warp_rows ? 8 : 32;
+    const int mchunk = warp_rows ? (lane & 3) : cchunk;
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     // this thread's two columns (gt, gt + 128) of the NEXT tile's add / mul vectors (every warp group stages its own copy)
     float a_nx[2] = {0.f, 0.f}, m_nx[2] = {1.f, 1.f};
@@ -437,7 +452,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
         uint32_t va[32];
         tmem_ld32(trow + c, va);
         // (A) this staging buffer is free again: the TMA store issued from it two sub-blocks ago has read it
-        if (warp_mode) {
+        if (sw_mode) {
+          mbar_wait(&store_done[grp * 2 + sbuf], ((nsub >> 1) & 1) ^ 1);
+        } else if (warp_mode) {
           if (lane == 0) bulk_wait_group_read<1>();
           __syncwarp();
         } else {
@@ -450,7 +467,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(stg + stg_off(mrow0 + mstep * i, mchunk)) = rres[i];
-          if (warp_mode) __syncwarp(); else group_barrier(4 + grp);
+          if (warp_rows) __syncwarp(); else group_barrier(4 + grp);
           // prefetch the residual of this group's next sub-block (the proxy fence below = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC
           // waits for these loads if they are still in flight; r2 ablation: most of the +5.6 us a residual costs on the
           // 64x64-level linears is its 21 MB of traffic, ~2 us is exposed latency)
@@ -532,7 +549,13 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
                            pack_bf16(f[3].x, f[3].y));
         }
         if (tre) p.trace[320 + (c >> 6) * 8 + 3] = clock64();
-        if (warp_mode) {
+        if (sw_mode) {
+          // (C) hand the staged rows to the group's store warp (release: proxy fence, then one arrive per warp)
+          fence_proxy_async_smem();                 // generic-proxy writes above -> visible to the async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&store_req[grp * 2 + sbuf]);
+          ++nsub;
+        } else if (warp_mode) {
           // (C) one TMA store per warp and sub-block: box (32 ch, 32 rows of this warp), clipped against the tensor
           fence_proxy_async_smem();                 // generic-proxy writes above -> visible to the async proxy
           __syncwarp();
@@ -639,7 +662,28 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       if constexpr (PAIR) mbar_arrive_cluster(&tempty_bar[as], 0); else mbar_arrive(&tempty_bar[as]);
       if (tracing && it < 8 && et == 0) p.trace[6 * 16 + it] = clock64();
     }
-    if (use_tma && (warp_mode ? lane == 0 : gt == 0)) bulk_wait_group_all();      // shared memory must outlive the last TMA stores
+    if (!sw_mode && use_tma && (warp_mode ? lane == 0 : gt == 0)) bulk_wait_group_all();      // shared memory must outlive the last TMA stores
+  } else if (LEAN) {
+    // =============================== TMA-store issuer of epilogue group g (lean kernel) ===============================
+    // walks the group's sub-block sequence (same tile order, same column order), one 128-row box per sub-block
+    const int g = warp - kStoreWarp0;
+    uint32_t nsub = 0;
+    int it = 0;
+    for (int t = u_first; t < total_tiles; t += u_stride, ++it) {
+      const TileCoord tc = tile_coord(p, t, n_tiles, BN, Wt, Ht, Bt, rank);
+      for (int c = ((g + it) & 1) * 32; c < BN; c += 64, ++nsub) {
+        const int b = nsub & 1;
+        mbar_wait(&store_req[g * 2 + b], (nsub >> 1) & 1);
+        if (lane == 0) {
+          tma_store_4d(&mapOut, staging + g * kEpiStageBytes + b * kEpiBufBytes, tc.n0 + c, tc.x0, tc.y0, tc.b0);
+          bulk_commit_group();
+          bulk_wait_group_read<0>();
+          mbar_arrive(&store_done[g * 2 + b]);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) bulk_wait_group_all();
   }
 
   tc_fence_before();
@@ -776,12 +820,11 @@ static int launch_p(const GemmParams& p, const CUtensorMap& a1, const CUtensorMa
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "conv_gemm_persistent launch");
 }
 
-static int g_lean_epilogue = getenv("UR_GEMM_LEAN") ? atoi(getenv("UR_GEMM_LEAN")) : 1;   // development: 0 = general kernel always
 
 int launch_conv_gemm_persistent(const GemmParams& p, const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& w,
                                 const CUtensorMap& mo, bool pair, int bn, int total_units, int n_tiles,
                                 cudaStream_t stream) {
-  const bool lean = g_lean_epilogue && p.act == UR_ACT_NONE && !p.chscale && p.alpha == 1.0f && p.tma_store == 2 && !p.ws;
+  const bool lean = p.tma_store == 4;          // chosen by the host together with the 128-row output box (ur_gemm.cu)
   if (pair) {
     switch (bn) {
       case 64: return lean ? launch_p<64, true, true>(p, a1, a2, w, mo, total_units, n_tiles, stream)
