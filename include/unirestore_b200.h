@@ -133,7 +133,9 @@ int ur_chan_stats(const void* x, int64_t ld, int64_t img_stride, int batch, int 
                   int stats_ld, int stats_off, int zero_first, void* stream);
 /* out = [silu]( (cat(x1,x2) - mean_g) * rstd_g * gamma + beta ), group statistics from ur_chan_stats (or from the
  * ur_conv_gemm epilogue).  stats2 == NULL: stats is [batch][c1+c2][2]; else stats is [batch][c1][2] and stats2 is
- * [batch][c2][2] (each source carries the statistics its producer accumulated). */
+ * [batch][c2][2] (each source carries the statistics its producer accumulated).
+ * gamma / beta are PARAMETERS: the kernel reads them before its programmatic-dependency wait, so they must not be
+ * written by a kernel launched just before on the same stream (x1, x2 and the statistics may be). */
 int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, const void* x2, int64_t ld2, int64_t is2, int c2,
                   const double* stats, const double* stats2, int groups, int batch, int pixels, const float* gamma, const float* beta,
                   float eps, int silu, void* out, int64_t ldo, int64_t iso, void* stream);

@@ -69,61 +69,93 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
                                   int CV, int PL, int chunk,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                                   bf16* __restrict__ out, long long ldo, long long iso) {
+  // The small tensors of the low-resolution levels (8 x 8 / 16 x 16 pixels, 1280..2560 channels: ~800 launches per
+  // forward) are a pure latency chain -- statistics -> group reduction -> affine parameters -> data -> store took 12 us
+  // for 10 MB (r2 chain benchmark).  So: the affine parameters (weights, not written by the predecessor) are fetched
+  // BEFORE the programmatic-dependency wait; the first batch of activations and the statistics leave together right
+  // after it (one L2 round trip instead of three); the fp64 group reduction runs on several threads per group.
   pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ __align__(16) double shd[];  // per-channel (sum, sumsq) [C][2] as doubles, then mean[G], rstd[G] floats
   float* sh = reinterpret_cast<float*>(shd + 2 * (C1 + C2));
   const int C = C1 + C2;
   const int cg = C / G;
   const int b = blockIdx.y;
-  // statistics of channel c: one array over cat(x1, x2), or one array per source.  Every thread fetches whole
-  // (sum, sumsq) pairs in ONE round trip to L2 (16-byte loads) -- a serial walk over the cg channels of a group by G
-  // threads cost cg dependent L2 latencies at the head of every block -- then G threads reduce from shared memory.
-  const double* st1 = stats + static_cast<long long>(b) * (stats2 ? C1 : C) * 2;
-  const double* st2 = stats2 ? stats2 + static_cast<long long>(b) * C2 * 2 - 2 * C1 : st1;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const double2 v = *reinterpret_cast<const double2*>((c < C1 ? st1 : st2) + 2 * c);
-    shd[2 * c] = v.x;
-    shd[2 * c + 1] = v.y;
-  }
-  __syncthreads();
-  const double inv_n = 1.0 / (static_cast<double>(P) * cg);
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double s = 0.0, q = 0.0;
-    for (int c = g * cg; c < (g + 1) * cg; ++c) {
-      s += shd[2 * c];
-      q += shd[2 * c + 1];
-    }
-    const double mean = s * inv_n;
-    double var = q * inv_n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    sh[g] = static_cast<float>(mean);
-    sh[G + g] = rsqrtf(static_cast<float>(var) + eps);
-  }
-  __syncthreads();
   const int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
   const int c0 = cv * 8;
-  float sc[8], sf[8];
+  float ga[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = c0 + j;
-    const int g = c / cg;
-    const float ga = gamma ? __ldg(gamma + c) : 1.f;
-    const float be = beta ? __ldg(beta + c) : 0.f;
-    sc[j] = sh[G + g] * ga;
-    sf[j] = be - sh[g] * sc[j];
+    ga[j] = gamma ? __ldg(gamma + c0 + j) : 1.f;
+    be[j] = beta ? __ldg(beta + c0 + j) : 0.f;
   }
+  pdl_wait();
   const bf16* src = (c0 < C1) ? (x1 + b * is1 + c0) : (x2 + b * is2 + (c0 - C1));
   const long long lds = (c0 < C1) ? ld1 : ld2;
   bf16* dst = out + b * iso + c0;
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(P, p0 + chunk);
-  // four independent 16-byte loads in flight per thread (the kernel is latency-bound otherwise)
-  for (int p = p0 + pl; p < p1; p += 4 * PL) {
-    uint4 v[4];
+  // first batch of this thread's pixels: four independent 16-byte loads in flight while the statistics arrive
+  uint4 v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      if (p + i * PL < p1) v[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p + i * PL) * lds));
+  for (int i = 0; i < 4; ++i)
+    if (p0 + pl + i * PL < p1) v[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p0 + pl + i * PL) * lds));
+  // statistics of channel c: one array over cat(x1, x2), or one array per source.  Every thread fetches whole
+  // (sum, sumsq) pairs in ONE round trip to L2 (16-byte loads), then TPG threads per group reduce from shared memory
+  // (a serial walk over the cg channels of a group by one thread was cg dependent fp64 adds at the head of every block)
+  const double* st1 = stats + static_cast<long long>(b) * (stats2 ? C1 : C) * 2;
+  const double* st2 = stats2 ? stats2 + static_cast<long long>(b) * C2 * 2 - 2 * C1 : st1;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double2 sv = *reinterpret_cast<const double2*>((c < C1 ? st1 : st2) + 2 * c);
+    shd[2 * c] = sv.x;
+    shd[2 * c + 1] = sv.y;
+  }
+  __syncthreads();
+  {
+    // TPG = 1, 2, 4 or 8 threads per group (a power of two: the partial sums meet by warp shuffles inside aligned lane
+    // clusters), as many as the block has: blockDim.x >= 32 always, G <= blockDim.x * ... handled by the outer loop
+    int tpg = 8;
+    while (tpg > 1 && G * tpg > static_cast<int>(blockDim.x & ~31u)) tpg >>= 1;
+    const double inv_n = 1.0 / (static_cast<double>(P) * cg);
+    const int slots = static_cast<int>(blockDim.x & ~31u) / tpg;          // groups handled per pass (whole warps only)
+    for (int g0 = 0; g0 < G; g0 += slots) {
+      const int g = g0 + static_cast<int>(threadIdx.x) / tpg, sub = threadIdx.x % tpg;
+      const bool active = threadIdx.x < (blockDim.x & ~31u) && g < G;
+      double s = 0.0, q = 0.0;
+      if (active) {
+        for (int c = g * cg + sub; c < (g + 1) * cg; c += tpg) {
+          s += shd[2 * c];
+          q += shd[2 * c + 1];
+        }
+      }
+      if (threadIdx.x < (blockDim.x & ~31u)) {         // whole warps: the shuffles below name every lane
+        for (int o = tpg >> 1; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+      }
+      if (active && sub == 0) {
+        const double mean = s * inv_n;
+        double var = q * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        sh[g] = static_cast<float>(mean);
+        sh[G + g] = rsqrtf(static_cast<float>(var) + eps);
+      }
+    }
+  }
+  __syncthreads();
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cg;
+    sc[j] = sh[G + g] * ga[j];
+    sf[j] = be[j] - sh[g] * sc[j];
+  }
+  for (int p = p0 + pl; p < p1; p += 4 * PL) {
+    if (p != p0 + pl) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (p + i * PL < p1) v[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(p + i * PL) * lds));
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (p + i * PL >= p1) break;
@@ -269,7 +301,8 @@ static void pick_block(int C, int P, int& CV, int& PL, int& chunk, int& nchunks,
   static const int waves = getenv("UR_NORM_WAVES") ? atoi(getenv("UR_NORM_WAVES")) : 8;
   const int target = max(1, (waves * num_sms()) / max(1, B));
   chunk = (P + target - 1) / target;
-  const int min_chunk = PL * 8;
+  static const int min_iters = getenv("UR_NORM_MIN_ITERS") ? atoi(getenv("UR_NORM_MIN_ITERS")) : 2;   // x 4 PL pixels per block at least
+  const int min_chunk = PL * 4 * min_iters;
   if (chunk < min_chunk) chunk = min_chunk;
   nchunks = (P + chunk - 1) / chunk;
 }
