@@ -181,8 +181,11 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
 // ------------------------------------------------------------------------------------ layernorm
 // One warp per R consecutive tokens; the rows live in registers (C <= 8*32*NV), exact two-pass mean / variance.
 // All R * NV 16-byte loads of a warp are issued before the first reduction (the kernel is latency-bound otherwise).
+// The rows stay PACKED (bf16, as loaded) and are unpacked in each of the three passes: held as fp32 they took twice
+// the registers, 4 blocks per SM fitted and the ~40 KB per SM in flight bounded the kernel at 3.2 TB/s (r2 chain
+// benchmark); the unpacking is two ALU instructions per pair.
 template <int NV, int R>
-__global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
+__global__ void __launch_bounds__(128, NV <= 2 ? 8 : 1) layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ out, long long ldo,
                                  int M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float eps) {
   pdl_launch_dependents();
@@ -191,7 +194,7 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
   const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
   if (row0 >= M) return;
   const int nvec = C >> 3;
-  float v[R][NV][8];
+  uint4 raw[R][NV];
   float sum[R], sq[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -199,20 +202,31 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
-      uint4 t = make_uint4(0u, 0u, 0u, 0u);
-      if (row_ok && vi < nvec) t = __ldg(reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + vi * 8));
-      const uint32_t u[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) unpack_bf16(u[j], v[r][i][2 * j], v[r][i][2 * j + 1]);
+      raw[r][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && vi < nvec) raw[r][i] = __ldg(reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + vi * 8));
     }
   }
+  // (volatile asm: the compiler would otherwise unpack once and keep -- or spill -- the fp32 copies)
+  auto unpack8 = [](const uint4& t, float* f) {
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t lo, hi;
+      asm volatile("shl.b32 %0, %2, 16;\n\tand.b32 %1, %2, 0xffff0000;" : "=r"(lo), "=r"(hi) : "r"(u[j]));
+      f[2 * j] = __uint_as_float(lo);
+      f[2 * j + 1] = __uint_as_float(hi);
+    }
+  };
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     sum[r] = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(raw[r][i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum[r] += v[r][i][j];          // padded vectors are zero
+      for (int j = 0; j < 8; ++j) sum[r] += f[j];          // padded vectors are zero
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -226,9 +240,11 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if (lane + 32 * i < nvec) {
+        float f[8];
+        unpack8(raw[r][i], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = v[r][i][j] - mean;
+          const float d = f[j] - mean;
           sq[r] += d * d;
         }
       }
@@ -253,11 +269,13 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, long long ldx, bf16
         if (row0 + r < M) {
           const float mean = sum[r];
           const float rstd = rsqrtf(sq[r] / C + eps);
+          float f[8];
+          unpack8(raw[r][i], f);
           uint32_t o[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float a = (v[r][i][2 * j] - mean) * rstd * ga[2 * j] + be[2 * j];
-            const float d = (v[r][i][2 * j + 1] - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1];
+            const float a = (f[2 * j] - mean) * rstd * ga[2 * j] + be[2 * j];
+            const float d = (f[2 * j + 1] - mean) * rstd * ga[2 * j + 1] + be[2 * j + 1];
             o[j] = pack_bf16(a, d);
           }
           *reinterpret_cast<uint4*>(out + (row0 + r) * ldo + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
