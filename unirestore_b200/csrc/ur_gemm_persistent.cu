@@ -336,7 +336,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
     const int mchunk = warp_rows ? (lane & 3) : cchunk;
     bf16* outp = reinterpret_cast<bf16*>(p.out);
     // this thread's two columns (gt, gt + 128) of the NEXT tile's add / mul vectors (every warp group stages its own copy)
-    float a_nx[2] = {0.f, 0.f}, m_nx[2] = {1.f, 1.f};
+    // (bias and row vector are kept as loaded and only added when they are staged, one tile later: `a += __ldg(...)`
+    //  made the add wait for the load right here, 500-1 000 cycles of exposed L2 latency per tile -- clock64 probes r2)
+    float a_nx[2] = {0.f, 0.f}, r_nx[2] = {0.f, 0.f}, m_nx[2] = {1.f, 1.f};
     auto fetch_vec = [&](const TileCoord& tn) {
       const int no0 = gated ? (tn.n0 >> 1) : tn.n0;
       const int bb = tn.b0 < p.B ? tn.b0 : p.B - 1;      // (a PAIR ghost tile lies past the last image)
@@ -344,12 +346,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
       for (int h = 0; h < 2; ++h) {
         const int col = gt + 128 * h;
         const int n = tn.n0 + col;
-        float a = 0.f;
-        if (col < BN && n < p.N) {
-          if (p.bias) a += __ldg(p.bias + n);
-          if (p.rowvec) a += __ldg(p.rowvec + bb * p.rowvec_sb + n);
-        }
-        a_nx[h] = a;
+        const bool okn = col < BN && n < p.N;
+        a_nx[h] = (okn && p.bias) ? __ldg(p.bias + n) : 0.f;
+        r_nx[h] = (okn && p.rowvec) ? __ldg(p.rowvec + bb * p.rowvec_sb + n) : 0.f;
         m_nx[h] = (has_mul && col < ncols && no0 + col < n_out) ? __ldg(p.chscale + bb * p.chscale_sb + no0 + col) : 1.f;
       }
     };
@@ -402,7 +401,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ GemmParams p, const __grid_c
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (gt + 128 * h < BN) {
-          add[gt + 128 * h] = a_nx[h];
+          add[gt + 128 * h] = a_nx[h] + r_nx[h];
           if (!LEAN) mul[gt + 128 * h] = m_nx[h];
         }
       }
