@@ -109,8 +109,10 @@ int ur_debug_set_gemm_pair_mode(int mode);
 /* Development: 0 disables split-K (ur_conv_desc.workspace is then ignored); returns the previous value. */
 int ur_debug_set_gemm_splitk(int on);
 /* Development: persistent-kernel epilogue stores: 0 = st.global, 1 = one TMA store per 128-row sub-block (group
- * barrier), 2 = one TMA store per epilogue warp (32-row boxes, no barrier on the store path; default); returns the
- * previous value. */
+ * barrier), 2 = default: one TMA store per epilogue warp (32-row boxes, no barrier on the store path) in the general
+ * kernel; launches whose epilogue is bias / residual / statistics only run the lean instantiation, whose stores are
+ * issued by one store warp per epilogue group (128-row boxes, mbarrier hand-off).  0 and 1 force the general kernel.
+ * Returns the previous value. */
 int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
 /* Development: attention kernel generation for head_dim 64 / 128: 1 = attention_kernel (default: two softmax threads per
