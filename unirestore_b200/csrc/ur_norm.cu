@@ -359,14 +359,36 @@ extern "C" int ur_norm_apply(const void* x1, int64_t ld1, int64_t is1, int c1, c
     return set_error(UR_ERR_ARG, "ur_norm_apply: bad arguments (C=%d+%d groups=%d)", c1, c2, groups);
   int CV, PL, chunk, nchunks;
   pick_block(C, pixels, CV, PL, chunk, nchunks, batch);
-  dim3 grid(nchunks, batch);
   static bool configured = false;
   if (!configured) {          // up to C = 8192 channels of fp64 statistics staged in shared memory
     cudaError_t e = cudaFuncSetAttribute(norm_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 136 * 1024);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(norm_apply)");
     configured = true;
   }
-  launch_kernel(norm_apply_kernel, dim3(grid), dim3(CV * PL), 2 * groups * sizeof(float) + 2 * static_cast<size_t>(C) * sizeof(double), stream, 
+  const size_t smem = 2 * groups * sizeof(float) + 2 * static_cast<size_t>(C) * sizeof(double);
+  // Grid = ONE full wave of resident blocks when the tensor is big enough for it (round 2, chain benchmark): with the
+  // "8 waves" rule the 64 x 64 level launched 688 blocks where 444 are resident (72 registers, 240 threads: 3 per SM) --
+  // 1.55 waves, the second one half empty: 14.1 -> 12.6 us (C = 320), 26.7 -> 21.4 (640), 24.6 -> 18.6 (1920 @ 32 x 32).
+  {
+    static int occ_cache[33][2];                  // [warps per block][smem class] -> resident blocks per SM (0 = not asked yet)
+    const int warps = (CV * PL + 31) / 32;
+    const int cls = smem > 24 * 1024 ? 1 : 0;
+    int bps = warps <= 32 ? occ_cache[warps][cls] : 0;
+    if (!bps) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, norm_apply_kernel, CV * PL, smem) != cudaSuccess || bps < 1) bps = 1;
+      if (warps <= 32 && !cls) occ_cache[warps][cls] = bps;      // (the large-smem class depends on C: not cached)
+    }
+    const int per_image = (bps * num_sms()) / (batch > 0 ? batch : 1);
+    if (per_image >= 1) {
+      const int one_wave = (pixels + per_image - 1) / per_image;          // pixels per block for exactly one wave
+      if (one_wave > chunk) {
+        chunk = one_wave;
+        nchunks = (pixels + chunk - 1) / chunk;
+      }
+    }
+  }
+  dim3 grid(nchunks, batch);
+  launch_kernel(norm_apply_kernel, dim3(grid), dim3(CV * PL), smem, stream, 
       static_cast<const bf16*>(x1), ld1, is1, c1, static_cast<const bf16*>(x2), ld2, is2, c2, stats, stats2, groups, pixels, CV,
       PL, chunk, gamma, beta, eps, silu, static_cast<bf16*>(out), ldo, iso);
   cudaError_t e = cudaGetLastError();
