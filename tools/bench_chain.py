@@ -17,10 +17,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--ring", default="1,2,6")
 ap.add_argument("--reps", type=int, default=48)
 ap.add_argument("--cases", default="")
+ap.add_argument("--pair", type=int, default=-1, help="CTA-pair mode: -1 library rule, 0 never, 1 whenever legal")
 ap.add_argument("--gbn", type=int, default=0, help="force the N tile of the gated cases (0 = library choice)")
 ap.add_argument("--bn", type=int, default=0, help="force the N tile of the non-gated cases (0 = library choice)")
 a = ap.parse_args()
 dev = "cuda:0"
+from unirestore_b200 import _cabi  # noqa: E402
+_cabi.lib().ur_debug_set_gemm_pair_mode(a.pair)
 CASES = [(32768, 320, 320, ops.UR_ACT_NONE, False, False, "lin64"), (32768, 320, 320, ops.UR_ACT_NONE, True, False, "lin64+res"),
          (32768, 320, 320, ops.UR_ACT_NONE, True, True, "lin64+res+stats"), (32768, 320, 960, ops.UR_ACT_NONE, False, False, "qkv64"),
          (32768, 320, 320, ops.UR_ACT_GELU, False, False, "gelu64"), (32768, 320, 2560, ops.UR_ACT_GEGLU, False, False, "geglu64"),
