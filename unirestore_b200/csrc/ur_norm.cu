@@ -163,15 +163,16 @@ __global__ void norm_apply_kernel(const bf16* __restrict__ x1, long long ld1, lo
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        // packed f32x2 arithmetic: one FMA for the pair, and the SiLU's multiplies / add around its two MUFU per element
         float a, c;
         unpack_bf16(u[j], a, c);
-        a = a * sc[2 * j] + sf[2 * j];
-        c = c * sc[2 * j + 1] + sf[2 * j + 1];
+        f2 y = fma2(f2{a, c}, f2{sc[2 * j], sc[2 * j + 1]}, f2{sf[2 * j], sf[2 * j + 1]});
         if (silu) {
-          a = silu_f(a);
-          c = silu_f(c);
+          const f2 t = mul2(y, splat2(-1.4426950408889634f));                   // -x log2(e)
+          const f2 d = fma2(f2{exp2_approx(t.x), exp2_approx(t.y)}, splat2(1.0f), splat2(1.0f));   // 1 + e^-x
+          y = mul2(y, f2{rcp_approx(d.x), rcp_approx(d.y)});
         }
-        o[j] = pack_bf16(a, c);
+        o[j] = pack_bf16(y.x, y.y);
       }
       *reinterpret_cast<uint4*>(dst + static_cast<long long>(p + i * PL) * ldo) = make_uint4(o[0], o[1], o[2], o[3]);
     }
