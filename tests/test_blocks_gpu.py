@@ -81,6 +81,28 @@ def test_upsample_subpixel():
     assert_close(nchw(m.run(nhwc(x))), o(x), TOL_BLOCK, "Upsample2D")
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 8, 12), (3, 8, 8), (1, 40, 24), (5, 4, 4)])
+def test_upsample_carries_fused_statistics(B, H, W):
+    """The four sub-pixel phase GEMMs accumulate the GroupNorm statistics of the up-sampled tensor into one buffer in their
+    epilogues (ragged tiles, 1 / 2 images per M tile); below 32 pixels per image the tensor carries none and its
+    consumer runs its own statistics pass."""
+    from unirestore_b200 import ops
+    from unirestore_b200.diffuie import sd_blocks as SB
+    torch.manual_seed(7)
+    m = SB.Upsample2D(64, True, 128).to(DEV)
+    x = rnd(6, B, 64, H, W).to(DEV)
+    y = m.run(nhwc(x))
+    st = getattr(y, "_ur_stats", None)
+    if H * W < 32:
+        assert st is None
+        return
+    ref = ops.chan_stats(y.contiguous())
+    torch.cuda.synchronize()
+    scale = ref.abs().amax().clamp_min(1e-9)
+    # (fp32 partial sums per tile in the epilogue, per pixel lane in the statistics pass: ~1e-7 apart)
+    assert ((st - ref).abs() / scale).max().item() < 1e-6, "fused up-sample statistics differ from a statistics pass"
+
+
 @pytest.mark.parametrize("c,heads,hw", [(256, 4, (8, 8)), (512, 4, (4, 6)), (512, 1, (8, 8)), (64, 1, (2, 2))])
 def test_spatial_attention(c, heads, hw):
     from oracle import blocks as OB

@@ -235,8 +235,15 @@ class Upsample2D(UrModule):
     def run(self, x):
         B, H, W, _ = x.shape
         out = torch.empty((B, 2 * H, 2 * W, self.out_channels), device=x.device, dtype=torch.bfloat16)
+        # GroupNorm statistics of the up-sampled tensor (its consumer is always a ResnetBlock2D): the four phase GEMMs
+        # accumulate into ONE buffer in their epilogues, so no ur_chan_stats pass reads the tensor again (the VAE's
+        # 512^2 x 128 outputs cost 126 us each that way).  The epilogue can only do it while an image contributes >= 32
+        # rows to an M tile (H * W >= 32); below that the consumer falls back to its own statistics pass.
+        stats = ops.new_stats(x.device, B, self.out_channels) if H * W >= 32 else None
         for (py, px), (taps, wp) in self.pk["phases"].items():
-            ops.conv_gemm(x, wp, self.out_channels, taps=taps, bias=self.pk["b"], out=out[:, py::2, px::2])
+            ops.conv_gemm(x, wp, self.out_channels, taps=taps, bias=self.pk["b"], out=out[:, py::2, px::2], stats=stats)
+        if stats is not None:
+            out._ur_stats = stats
         return out
 
 
