@@ -1,9 +1,9 @@
 """CFRM building block ``AdaNAFV2`` -- reference cfrm.py:12-54.
 
     t = conv_in(x)                   c -> 4c                 tcgen05 GEMM
-    t = GroupNorm(16)(t)                                      ur_chan_stats + ur_norm_apply
+    t = GroupNorm(16)(t)                                      epilogue statistics + ur_norm_apply
     u = gelu(group_conv3x3(t))       16 groups                grouped implicit GEMM (+GELU epilogue)
-    u = u * intra(GAP(u)) ; u = u * inter(GAP(u)) per group   ur_chan_stats + ur_adanaf_scales + ur_scale_channels
+    u = u * intra(GAP(u)) ; u = u * inter(GAP(u)) per group   epilogue sums + ur_adanaf_scales + ur_scale_channels
     y = x + pwconv(u)                4c -> c                  GEMM (+residual)
     out = NAFBlock(y)
 Groups narrower than the 64-channel K block of the GEMM kernel (c = 128 -> 32 channels per group) are packed
@@ -62,11 +62,12 @@ class AdaNAFV2(UrModule):
     def run(self, x):
         p = self.pk
         B, H, W, _ = x.shape
-        t = ops.conv_gemm(x, p["wi"], self.wide, bias=p["bi"])
+        t = ops.conv_gemm(x, p["wi"], self.wide, bias=p["bi"], want_stats=True)     # GroupNorm statistics from the epilogue
         t = ops.group_norm(t, self.groups, p["gn_g"], p["gn_b"], p["gn_eps"])
         u = ops.conv_gemm(t, p["wg"], self.wide, taps=ops.TAPS_3x3, bias=p["bg"], act=ops.UR_ACT_GELU,
-                          group_kc=p["kg"], group_nc=p["kg"], bn=p["bn_g"])
-        scale = ops.adanaf_scales(ops.chan_stats(u), H * W, self.groups, p["w_intra"], p["b_intra"], p["w_inter"],
+                          group_kc=p["kg"], group_nc=p["kg"], bn=p["bn_g"], want_stats=True)
+        # the global average pool reads the channel sums the GEMM epilogue accumulated (no pass over u)
+        scale = ops.adanaf_scales(u._ur_stats, H * W, self.groups, p["w_intra"], p["b_intra"], p["w_inter"],
                                   p["b_inter"])
         ops.scale_channels_(u, scale)
         y = ops.conv_gemm(u, p["wp"], self.c, bias=p["bp"], residual=x)

@@ -3,7 +3,7 @@
 On bf16 channels-last tensors (``x [B,s,s,c_out]``, ``skip [B,s,s,c]``) and an fp32 prompt ``cond [B,T,D=c]``:
     sn   = InstanceNorm(skip)                      shared by the three gate branches (affine=False): stats + apply
     h    = gelu(conv3x3_{f,i,c}(sn))   c -> 3c     ONE implicit GEMM, the three first convs stacked along N
-    pool = GAP(conv3x3_{f,i,c}(h))     3 groups    ONE grouped implicit GEMM + ur_chan_stats
+    pool = GAP(conv3x3_{f,i,c}(h))     3 groups    ONE grouped implicit GEMM (channel sums from its epilogue)
     f,i  = softmax(pool_f), softmax(pool_i); cval = tanh(pool_c); cond' = f*cond + i*cval
     o    = tanh(out_gate(cond')); cond_next = gelu(prompt_trans(cond'))          ur_tfa_gates (one tiny kernel)
     skip = skip + t_gate2(o * t_gate1(skip))       two GEMMs (per-image channel scale / residual epilogues)
@@ -62,13 +62,14 @@ class TaskFeatureAdapter(UrModule):
         h = ops.conv_gemm(sn, p["w_a"], 3 * c, taps=ops.TAPS_3x3, bias=p["b_a"], act=ops.UR_ACT_GELU)
         if p["bn_b"]:
             g = ops.conv_gemm(h, p["w_b"], 3 * hid, taps=ops.TAPS_3x3, bias=p["b_b"], group_kc=c, group_nc=hid,
-                              bn=p["bn_b"])
+                              bn=p["bn_b"], want_stats=True)      # channel sums for the pooled gates from the epilogue
         else:       # narrow (test) configurations: one launch per branch on channel-slice views
             g = torch.empty((B, H, W, 3 * hid), device=x.device, dtype=torch.bfloat16)
             for i in range(3):
                 ops.conv_gemm(h[..., i * c:(i + 1) * c], p["w_b"][i * hid:(i + 1) * hid], hid, taps=ops.TAPS_3x3,
                               bias=p["b_b"][i * hid:(i + 1) * hid].contiguous(), out=g[..., i * hid:(i + 1) * hid])
-        o, cond_next = ops.tfa_gates(ops.chan_stats(g), H * W, cond.float().contiguous(), p["w_og"], p["b_og"],
+        gst = getattr(g, "_ur_stats", None)
+        o, cond_next = ops.tfa_gates(gst if gst is not None else ops.chan_stats(g), H * W, cond.float().contiguous(), p["w_og"], p["b_og"],
                                      p.get("w_pt"), p.get("b_pt"))
         tg = ops.conv_gemm(skip, p["w_t1"], self.prompt_dim, bias=p["b_t1"], chscale=o)
         skip2 = ops.conv_gemm(tg, p["w_t2"], c, bias=p["b_t2"], residual=skip)
