@@ -289,24 +289,24 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   return d;
 }
 __device__ __forceinline__ f2 splat2(float v) { return f2{v, v}; }
-// exact-erf GELU of a pair: the arithmetic of gelu_erf_f (Abramowitz-Stegun 7.1.26) with the polynomial, the argument
-// products and the final combination on packed instructions; 4 MUFU (2 rcp, 2 ex2) + ~9 packed + 4 scalar ops per pair
+// exact-erf GELU of a pair: Abramowitz-Stegun 7.1.26 as in gelu_erf_f, with the constants of the argument scaling folded
+// (|x| / sqrt2 * p and -x^2 / 2 * log2 e come straight from x), the sign handled by 0.5 x (1 + erf) = hx + |hx| erf(|xs|),
+// and everything but the 4 MUFU (2 rcp, 2 ex2) on packed instructions: 11 packed + 4 MUFU issue slots per pair (15 + 4
+// scalar before; the GEGLU epilogue is bound by issue slots -- profiles/epilogue_store_experiments_r2.txt, experiment 9)
 __device__ __forceinline__ f2 gelu_erf2(f2 x) {
-  const f2 xs = mul2(x, splat2(0.70710678118654752f));
-  const f2 ax = f2{fabsf(xs.x), fabsf(xs.y)};
-  const f2 den = fma2(ax, splat2(0.3275911f), splat2(1.0f));
+  const f2 ax = f2{fabsf(x.x), fabsf(x.y)};
+  const f2 den = fma2(ax, splat2(0.3275911f * 0.70710678118654752f), splat2(1.0f));              // 1 + p |x| / sqrt2
   const f2 t = f2{rcp_approx(den.x), rcp_approx(den.y)};
   f2 pl = fma2(t, splat2(1.061405429f), splat2(-1.453152027f));
   pl = fma2(pl, t, splat2(1.421413741f));
   pl = fma2(pl, t, splat2(-0.284496736f));
   pl = fma2(pl, t, splat2(0.254829592f));
-  const f2 nx2 = mul2(ax, f2{-ax.x * 1.4426950408889634f, -ax.y * 1.4426950408889634f});      // -x^2 log2(e)
+  const f2 nx2 = mul2(mul2(x, x), splat2(-0.5f * 1.4426950408889634f));                          // -(x^2 / 2) log2(e)
   const f2 e = f2{exp2_approx(nx2.x), exp2_approx(nx2.y)};
   const f2 pt = mul2(pl, t);
-  const f2 y = fma2(f2{-pt.x, -pt.y}, e, splat2(1.0f));                                         // erf(|x|)
-  const f2 erfv = f2{copysignf(y.x, xs.x), copysignf(y.y, xs.y)};
+  const f2 y = fma2(f2{-pt.x, -pt.y}, e, splat2(1.0f));                                         // erf(|x| / sqrt2)
   const f2 hx = mul2(x, splat2(0.5f));
-  return fma2(hx, erfv, hx);                                                                      // 0.5 x (1 + erf)
+  return fma2(f2{fabsf(hx.x), fabsf(hx.y)}, y, hx);                                             // 0.5 x (1 + erf(x / sqrt2))
 }
 
 // 16-byte vector reduction into global memory (sm_90+): four fp32 adds in one L2 atomic transaction
