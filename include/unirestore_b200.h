@@ -115,6 +115,9 @@ int ur_debug_set_gemm_splitk(int on);
  * Returns the previous value. */
 int ur_debug_set_gemm_tma_store(int on);
 int ur_debug_set_attention_trace(void* buf);   /* 64 int64 */
+/* Development: 0 = head_dim 64 launches whose keys fit one 128-key tile (cross-attention on the prompt) run the general
+ * kernel instead of the query-tile-loop kernel; returns the previous value. */
+int ur_debug_set_attention_kv1(int on);
 /* Development: attention kernel generation for head_dim 64 / 128: 1 = attention_kernel (default: two softmax threads per
  * row, two CTAs per SM), 2 = attention2_kernel (two query tiles per CTA, one softmax thread per row, single TMEM pass, P in
  * tensor memory, exp2 partly on the FMA pipe; measured equal, profiles/attention_experiments_r2.txt); returns the previous

@@ -24,20 +24,25 @@ def _ref(q, k, v, heads):
     return bf16_round(o.transpose(1, 2).reshape(B, Tq, C))
 
 
-@pytest.fixture(params=[1, 2], ids=["attention1", "attention2"])
+@pytest.fixture(params=[(1, 1), (2, 1), (1, 0)], ids=["attention1+kv1", "attention2", "attention1-general"])
 def impl(request):
-    """Both kernel generations in the tree: attention_kernel (default) and attention2_kernel."""
+    """The kernels in the tree: attention_kernel (default) with the query-tile-loop kernel for launches whose keys fit
+    one tile (attention_kv1_kernel, default), attention2_kernel, and attention_kernel alone."""
     from unirestore_b200 import _cabi
-    old = _cabi.lib().ur_debug_set_attention_impl(request.param)
-    yield request.param
+    gen, kv1 = request.param
+    old = _cabi.lib().ur_debug_set_attention_impl(gen)
+    old_kv1 = _cabi.lib().ur_debug_set_attention_kv1(kv1)
+    yield gen
     _cabi.lib().ur_debug_set_attention_impl(old)
+    _cabi.lib().ur_debug_set_attention_kv1(old_kv1)
 
 
 @pytest.mark.parametrize("B,heads,d,Tq,Tk", [(2, 5, 64, 256, 256), (1, 2, 64, 128, 128), (2, 4, 64, 200, 300),
                                              (1, 5, 64, 4096, 4096), (2, 4, 128, 64, 64), (3, 4, 128, 256, 256),
                                              (2, 20, 64, 4, 4), (1, 10, 64, 1024, 1024), (2, 1, 64, 130, 7),
                                              (1, 3, 64, 384, 1000), (2, 2, 64, 129, 129), (1, 2, 128, 300, 200),
-                                             (1, 1, 64, 256, 33)])
+                                             (1, 1, 64, 256, 33), (8, 5, 64, 4096, 77), (3, 7, 64, 1000, 128),
+                                             (2, 3, 64, 777, 1), (1, 40, 64, 128, 100)])
 def test_fused_self_attention_packed_qkv(impl, B, heads, d, Tq, Tk):
     from unirestore_b200 import ops
     torch.backends.cuda.matmul.allow_tf32 = False

@@ -13,13 +13,16 @@ ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--cases", default="self64,self32,cross64,ctrl64")
 ap.add_argument("--poly", type=int, default=3, help="exp2 pairs of every 8 on the FMA pipe (attention2)")
 ap.add_argument("--impl", type=int, default=2, help="attention kernel generation (1 or 2)")
+ap.add_argument("--kv1", type=int, default=1, help="query-tile-loop kernel for single-KV-tile launches")
+ap.add_argument("--graph", action="store_true", help="time 32 launches inside one CUDA graph (no host gaps)")
 a = ap.parse_args()
 from unirestore_b200 import _cabi  # noqa: E402
 _cabi.lib().ur_debug_set_attention_impl(a.impl)
 _cabi.lib().ur_debug_set_attention_poly(a.poly)
+_cabi.lib().ur_debug_set_attention_kv1(a.kv1)
 CASES = {"self64": (8, 5, 64, 4096, 4096), "self32": (8, 10, 64, 1024, 1024), "cross64": (8, 5, 64, 4096, 77),
          "ctrl64": (8, 4, 64, 4096, 4096), "self16": (8, 20, 64, 256, 256), "self128": (4, 5, 64, 16384, 16384),
-         "ctrl128": (8, 4, 128, 256, 256)}
+         "ctrl128": (8, 4, 128, 256, 256), "cross32": (8, 10, 64, 1024, 77), "cross16": (8, 20, 64, 256, 77)}
 dev = "cuda:0"
 for name in a.cases.split(","):
     B, h, d, Tq, Tk = CASES[name]
@@ -33,11 +36,26 @@ for name in a.cases.split(","):
         ops.attention(q, k, v, h, out=out)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(a.iters):
-        ops.attention(q, k, v, h, out=out)
-    e.record()
-    torch.cuda.synchronize()
-    t = s.elapsed_time(e) * 1e-3 / a.iters
+    if a.graph:
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(32):
+                    ops.attention(q, k, v, h, out=out)
+        g.replay()
+        torch.cuda.synchronize()
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        t = s.elapsed_time(e) * 1e-3 / 32
+    else:
+        s.record()
+        for _ in range(a.iters):
+            ops.attention(q, k, v, h, out=out)
+        e.record()
+        torch.cuda.synchronize()
+        t = s.elapsed_time(e) * 1e-3 / a.iters
     fl = 4.0 * B * Tq * Tk * C
     print("impl%d poly%d %-8s B=%d h=%d d=%d Tq=%d Tk=%d  %8.1f us  %7.1f TF/s" % (a.impl, a.poly, name, B, h, d, Tq, Tk, t * 1e6, fl / t / 1e12), flush=True)

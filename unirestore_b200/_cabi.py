@@ -58,6 +58,7 @@ SIGNATURES = {
     "ur_debug_set_gemm_tma_store": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_trace": (C.c_int, [_P]),
     "ur_debug_set_attention_impl": (C.c_int, [C.c_int]),
+    "ur_debug_set_attention_kv1": (C.c_int, [C.c_int]),
     "ur_debug_set_attention_poly": (C.c_int, [C.c_int]),
     "ur_chan_stats": (C.c_int, [_P, _I64, _I64, _I, _I, _I, _P, _I, _I, _I, _P]),
     "ur_group_norm": (C.c_int, [_P, _I64, _I64, _I, _P, _I64, _I64, _I, _I, _I, _I, _P, _P, _F, _I, _P, _I64, _I64, _P]),

@@ -901,6 +901,289 @@ static int launch_attention512(const AttnParams& p, const CUtensorMap& mq, const
   return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention512 launch");
 }
 
+// =====================================================================================================================
+// attention_kv1_kernel: head_dim 64, ALL keys in one 128-key tile (cross-attention on the 77-token prompt:
+// base_model.py:159 attn2 -- 300 launches per forward).  The general kernel spends one CTA per 128 queries, and with a
+// single KV tile a CTA is nothing but prologue + three dependent latencies (26 us for 4096 x 77, B = 8, 5 heads).  Here
+// a CTA keeps K / V resident and LOOPS over `nq` consecutive query tiles of its (image, head): Q tiles stream through a
+// 2-stage ring, S_{i+1} = Q_{i+1} K^T runs on the tensor core while the softmax threads finish tile i, and there is no
+// running maximum / rescaling at all.  One softmax thread per query row (4 warps), two TMEM passes over its <= 128
+// scores; the thread that wrote P_i also reads O_i = P_i V back, scales by 1 / l and stores its 128-byte output row,
+// so S, O and the P tile need no double buffering (a thread starts tile i+1 only after it has seen O_i).
+// smem: K 16 KB + V 16 KB + Q 2 x 16 KB + P 32 KB; TMEM: S 128 + O 64 columns -> two CTAs per SM.
+__global__ void __launch_bounds__(192, 2)
+attention_kv1_kernel(const __grid_constant__ AttnParams p, const __grid_constant__ CUtensorMap mapQ,
+                     const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapV, int nq) {
+  constexpr int D = 64;
+  constexpr int kQBytes = kTileQ * D * 2, kKBytes = kTileK * D * 2, kPBytes = kTileQ * kTileK * 2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kKBytes;
+  uint8_t* sQ = sV + kKBytes;                       // [2] stages
+  uint8_t* sP = sQ + 2 * kQBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;                      // [2]
+  uint64_t* q_empty = bars + 3;                     // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* o_full = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = warp_uniform(static_cast<int>(threadIdx.x >> 5)), lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int tiles = (p.Tq + kTileQ - 1) / kTileQ;
+  const int t0 = blockIdx.x * nq;                                  // first query tile of this CTA
+  const int n_my = min(nq, tiles - t0);                            // (host: t0 < tiles for every block)
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = warp_uniform(*tmem_slot);
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    const int bk = p.kv_shared ? 0 : b;
+    if (elect_one_sync()) {
+      mbar_expect_tx(kv_full, 2 * kKBytes);
+      tma_load_3d(sK, &mapK, kv_full, h * D, 0, bk);
+      tma_load_3d(sV, &mapV, kv_full, h * D, 0, bk);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i & 1;
+      mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&q_full[s], kQBytes);
+        tma_load_3d(sQ + s * kQBytes, &mapQ, &q_full[s], h * D, (t0 + i) * kTileQ, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 64, 1);     // B (= V) is MN-major
+    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aK = smem_u32(sK), aV = smem_u32(sV);
+    const int ksteps = (min(p.Tk, kTileK) + 15) >> 4;              // 16-key steps of P V that hold real keys
+    auto issue_s = [&](int i) {
+      const int s = i & 1;
+      mbar_wait(&q_full[s], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tmem_S, umma_desc_k_sw128(aQ + s * kQBytes) + 2 * k, umma_desc_k_sw128(aK) + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        tc_commit(s_full);
+        tc_commit(&q_empty[s]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    if (n_my > 0) issue_s(0);
+    for (int i = 0; i < n_my; ++i) {
+      if (i + 1 < n_my) {
+        mbar_wait(s_empty, i & 1);                  // every softmax thread holds its last S_i chunk in registers
+        issue_s(i + 1);
+      }
+      mbar_wait(p_full, i & 1);                     // P_i is in shared memory (and O_{i-1} has been read by its rows' threads)
+      tc_fence_after();
+      if (elect_one_sync()) {
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = umma_desc_k_sw128(aP + (k >> 2) * (kTileQ * 128)) + 2 * (k & 3);
+          const uint64_t db = umma_desc_mn_sw128(aV + k * 16 * 128, kTileK * 128);
+          tc_mma_bf16(tmem_O, da, db, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        tc_commit(o_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== softmax + output: one thread per query row ===============================
+    const int qd = warp & 3;                          // TMEM lane quarter of this warp (warps 2..5 -> 2, 3, 0, 1)
+    const int r = qd * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t tS = tmem_S + lane_off, tO = tmem_O + lane_off;
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    const int tk = min(p.Tk, kTileK);
+    const int nchunk = (tk + 31) >> 5;                // 32-column score chunks that hold real keys
+    for (int i = 0; i < n_my; ++i) {
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      float l0 = 0.f, l1 = 0.f;
+      if (nchunk <= 3) {
+        // ---- the prompt case (<= 96 keys): ONE TMEM pass, the whole score row in registers; S is released to the MMA
+        //      warp before any arithmetic.  Chunks below nchunk - 1 are full (no key masking).
+        uint32_t v[3][32];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < nchunk) tmem_ld32(tS + c * 32, v[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(s_empty);
+        float raw = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c < nchunk - 1) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) raw = max3(raw, __uint_as_float(v[c][j]), __uint_as_float(v[c][j + 1]));
+          } else if (c == nchunk - 1) {
+            const int kv = tk - c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < kv) raw = fmaxf(raw, __uint_as_float(v[c][j]));
+          }
+        }
+        const float nmx = -raw * p.scale_log2;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c < nchunk) {
+            const int kv = tk - c * 32;
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a0, a1;
+              fma2(a0, a1, __uint_as_float(v[c][2 * j]), __uint_as_float(v[c][2 * j + 1]), p.scale_log2, nmx);
+              float p0 = exp2_approx(a0), p1 = exp2_approx(a1);
+              if (c == nchunk - 1) {                 // (warp-uniform) only the last chunk can hold keys that do not exist
+                p0 = (2 * j < kv) ? p0 : 0.f;
+                p1 = (2 * j + 1 < kv) ? p1 : 0.f;
+              }
+              add2(l0, l1, l0, l1, p0, p1);
+              pk[j] = pack_bf16(p0, p1);
+            }
+            uint8_t* prow = sP + (c >> 1) * (kTileQ * 128) + r * 128;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
+              *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+            }
+          }
+        }
+      } else {
+        // ---- pass 1: row maximum of the raw scores
+        float raw = -INFINITY;
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + c * 32, v);
+          tmem_ld_wait();
+          const int kv = tk - c * 32;
+  #pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < kv) raw = fmaxf(raw, __uint_as_float(v[j]));
+        }
+        const float nmx = -raw * p.scale_log2;
+        // ---- pass 2: P = exp2(s * scale - max) -> bf16 -> shared memory (K-major SW128), row sum
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + c * 32, v);
+          tmem_ld_wait();
+          if (c == nchunk - 1) {                        // S_i is fully consumed: the MMA warp may overwrite it with S_{i+1}
+            tc_fence_before();
+            mbar_arrive(s_empty);
+          }
+          const int kv = tk - c * 32;
+          uint32_t pk[16];
+  #pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = (2 * j < kv) ? exp2_approx(fmaf(__uint_as_float(v[2 * j]), p.scale_log2, nmx)) : 0.f;
+            const float p1 = (2 * j + 1 < kv) ? exp2_approx(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2, nmx)) : 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[j] = pack_bf16(p0, p1);
+          }
+          // keys [32 c, 32 c + 32) = 4 chunks of 16 B at chunk index (c & 1) * 4 + q of row r in key block c >> 1
+          uint8_t* prow = sP + (c >> 1) * (kTileQ * 128) + r * 128;
+  #pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + qq) ^ swz;
+            *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * qq], pk[4 * qq + 1], pk[4 * qq + 2], pk[4 * qq + 3]);
+          }
+        }
+
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      // ---- O_i = P_i V: normalise and store this thread's row (64 bf16 = 128 contiguous bytes)
+      const float inv = 1.f / (l0 + l1);
+      mbar_wait(o_full, i & 1);
+      tc_fence_after();
+      const int q = (t0 + i) * kTileQ + r;
+      bf16* op = p.out + b * p.out_bs + static_cast<long long>(q) * p.ldo + h * D;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_ld_wait();
+        if (q < p.Tq) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(o[8 * j]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+            w.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+            w.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+            w.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+            reinterpret_cast<uint4*>(op)[c * 4 + j] = w;
+          }
+        }
+      }
+      tc_fence_before();       // the O reads above are ordered before the next p_full arrive (-> before P_{i+1} V overwrites O)
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+static int launch_attention_kv1(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                                cudaStream_t stream) {
+  constexpr int smem = 2 * kTileK * 64 * 2 + 2 * kTileQ * 64 * 2 + kTileQ * kTileK * 2 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(attention_kv1)");
+    configured = true;
+  }
+  // query tiles per CTA: one wave of 2 CTAs per SM over all (image, head, tile) units
+  const int tiles = (p.Tq + kTileQ - 1) / kTileQ;
+  const long long total = static_cast<long long>(tiles) * p.heads * p.batch;
+  int nq = static_cast<int>((total + 2LL * num_sms() - 1) / (2LL * num_sms()));
+  static const int force_nq = getenv("UR_ATTN_NQ") ? atoi(getenv("UR_ATTN_NQ")) : 0;     // development
+  if (force_nq > 0) nq = force_nq;
+  if (nq < 1) nq = 1;
+  if (nq > tiles) nq = tiles;
+  dim3 grid((tiles + nq - 1) / nq, p.heads, p.batch);
+  cudaError_t e = launch_kernel(attention_kv1_kernel, grid, dim3(192), smem, stream, p, mq, mk, mv, nq);
+  return e == cudaSuccess ? UR_OK : set_cuda_error(e, "attention_kv1 launch");
+}
+
 template <int D>
 static int launch_attention(const AttnParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                             dim3 grid, cudaStream_t stream) {
@@ -928,6 +1211,12 @@ static int make_qkv_map(CUtensorMap* m, const void* ptr, int width, int64_t ld, 
 using namespace ur;
 
 static long long* g_attn_trace = nullptr;
+static int g_attn_kv1 = 1;       // 1: head_dim 64 with all keys in one tile takes attention_kv1_kernel (query-tile loop)
+extern "C" int ur_debug_set_attention_kv1(int on) {
+  const int old = g_attn_kv1;
+  g_attn_kv1 = on;
+  return old;
+}
 static int g_attn_impl = 1;      // 1: attention_kernel (default: measured faster, r2c2); 2: attention2_kernel
 static int g_attn_poly = kPolyOf8Default;
 // development: exponential pairs (of every 8) evaluated by the FMA-pipe polynomial in attention2_kernel (0..3)
@@ -990,6 +1279,7 @@ extern "C" int ur_attention(const void* q, int64_t ldq, int64_t q_bs, const void
       default: return launch_attention2<64, 2, 3>(p, mq, mk, mv, stream);
     }
   }
+  if (head_dim == 64 && tk <= kTileK && g_attn_kv1) return launch_attention_kv1(p, mq, mk, mv, stream);
   dim3 grid((tq + kTileQ - 1) / kTileQ, heads, batch);
   return head_dim == 64 ? launch_attention<64>(p, mq, mk, mv, grid, stream)
                         : launch_attention<128>(p, mq, mk, mv, grid, stream);
